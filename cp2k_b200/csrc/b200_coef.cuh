@@ -1,0 +1,626 @@
+// Coefficient kernels of the B200 grid backend:
+//   pab_to_coef : density block -> per-task polynomial coefficients  (collocate)
+//   coef_to_hab : per-task coefficients -> Hamiltonian block, forces, virial
+//
+// Reference semantics restated here (paths relative to /root/reference/src/grid):
+//   load_pab / store_hab            ref/grid_ref_task_list.c:237-271, 462-499
+//   prepare_pab (35 grid_func's)    common/grid_prepare_pab.h:33-430, 447-517
+//   cab <-> cxyz re-centring        ref/grid_ref_collint.h:827-911
+//   cxyz <-> cijk (general cells)   ref/grid_ref_collint.h:697-762
+//   hab / forces / virial           common/grid_process_vab.h:29-251,
+//                                   ref/grid_ref_integrate.c:44-152
+// Unlike the reference GPU backend (gpu/grid_gpu_collocate.cu:34-118) the
+// decontraction is two-staged through shared memory, the density transforms
+// are generated from a small operator algebra instead of one routine per
+// grid_func, and a whole atom-pair block is accumulated in shared memory and
+// flushed once.
+#pragma once
+#include "b200_internal.cuh"
+
+namespace b200 {
+
+__constant__ OrbTable c_orb;
+__constant__ double c_binom[kMaxLSide + 1][kMaxLSide + 1];
+
+struct Orb {
+  int l[3];
+};
+__device__ inline Orb orb_of(const int c) {
+  return Orb{{c_orb.l[c][0], c_orb.l[c][1], c_orb.l[c][2]}};
+}
+__device__ inline int oidx(const Orb &a) { return coset(a.l[0], a.l[1], a.l[2]); }
+__device__ inline Orb oup(const int i, Orb a) {
+  a.l[i] += 1;
+  return a;
+}
+__device__ inline Orb odn(const int i, Orb a) {
+  a.l[i] = max(0, a.l[i] - 1);
+  return a;
+}
+
+// ---------------------------------------------------------------------------
+// Operator algebra for the density transforms.  A primitive Cartesian Gaussian
+// g(l) with exponent z obeys  d/dx_i g(l) = l_i g(l-e_i) - 2 z g(l+e_i)  and
+// x_j g(l) = g(l+e_j); each grid_func is a short sum of
+// (operator on a) x (operator on b).
+// ---------------------------------------------------------------------------
+enum OpKind : int { OP_ID = 0, OP_D, OP_N, OP_DD, OP_RD, OP_R, OP_CORE };
+struct Op {
+  int k, i, j;
+};
+struct FuncTerm {
+  double c;
+  Op a, b;
+};
+struct FuncDesc {
+  int nterms;
+  FuncTerm t[3];
+  int dla_max, dla_min, dlb_max, dlb_min;
+};
+
+// Host+device so the host can size buffers from the same table.
+__host__ __device__ inline bool describe_func(const int func, FuncDesc &F) {
+  const Op ID = {OP_ID, 0, 0};
+  F.nterms = 0;
+  F.dla_max = +1, F.dla_min = -1, F.dlb_max = +1, F.dlb_min = -1;
+  auto add = [&](double c, Op a, Op b) { F.t[F.nterms++] = FuncTerm{c, a, b}; };
+  if (func == 100) {
+    F.dla_max = F.dla_min = F.dlb_max = F.dlb_min = 0;
+    add(1.0, ID, ID);
+  } else if (func == 200) {
+    for (int i = 0; i < 3; i++)
+      add(0.5, Op{OP_D, i, 0}, Op{OP_D, i, 0});
+  } else if (func >= 301 && func <= 303) {
+    const int i = func - 301;
+    add(+1.0, ID, Op{OP_D, i, 0});
+    add(-1.0, Op{OP_D, i, 0}, ID);
+  } else if (func >= 411 && func <= 433) {
+    const int i = (func - 400) / 10 - 1, j = (func - 400) % 10 - 1;
+    if (i < 0 || i > 2 || j < 0 || j > 2)
+      return false;
+    F.dlb_max = +2;
+    add(+1.0, ID, Op{OP_RD, i, j});
+    add(-1.0, Op{OP_D, i, 0}, Op{OP_R, 0, j});
+  } else if (func >= 501 && func <= 503) {
+    const int i = func - 501;
+    add(1.0, ID, Op{OP_D, i, 0});
+    add(1.0, Op{OP_D, i, 0}, ID);
+  } else if (func >= 601 && func <= 603) {
+    const int i = func - 601;
+    add(1.0, Op{OP_D, i, 0}, Op{OP_D, i, 0});
+  } else if (func >= 701 && func <= 703) {
+    const int i = func - 701, j = (i + 1) % 3;
+    F.dla_max = +2, F.dla_min = -2, F.dlb_max = +2, F.dlb_min = -2;
+    add(1.0, Op{OP_DD, i, j}, Op{OP_DD, i, j});
+  } else if (func >= 801 && func <= 803) {
+    const int i = func - 801;
+    F.dla_max = +2, F.dla_min = -2, F.dlb_max = +2, F.dlb_min = -2;
+    add(1.0, Op{OP_DD, i, i}, Op{OP_DD, i, i});
+  } else if (func >= 901 && func <= 903) {
+    add(1.0, Op{OP_N, func - 901, 0}, ID);
+  } else if (func >= 904 && func <= 906) {
+    add(1.0, ID, Op{OP_N, func - 904, 0});
+  } else if (func >= 1001 && func <= 1003) {
+    add(1.0, Op{OP_CORE, func - 1001, 0}, ID);
+  } else {
+    return false;
+  }
+  return true;
+}
+
+struct OpTerm {
+  Orb o;
+  double c;
+};
+__device__ inline int op_expand(const Op op, const Orb l, const double z,
+                                OpTerm out[4]) {
+  const int i = op.i, j = op.j;
+  switch (op.k) {
+  case OP_ID:
+    out[0] = {l, 1.0};
+    return 1;
+  case OP_D:
+    out[0] = {odn(i, l), (double)l.l[i]};
+    out[1] = {oup(i, l), -2.0 * z};
+    return 2;
+  case OP_N:
+    out[0] = {odn(i, l), -(double)l.l[i]};
+    out[1] = {oup(i, l), 2.0 * z};
+    return 2;
+  case OP_DD:
+    if (i != j) {
+      out[0] = {odn(i, odn(j, l)), (double)(l.l[i] * l.l[j])};
+      out[1] = {oup(i, odn(j, l)), -2.0 * z * l.l[j]};
+      out[2] = {odn(i, oup(j, l)), -2.0 * z * l.l[i]};
+      out[3] = {oup(i, oup(j, l)), 4.0 * z * z};
+      return 4;
+    }
+    out[0] = {odn(i, odn(i, l)), (double)(l.l[i] * (l.l[i] - 1))};
+    out[1] = {l, -2.0 * z * (2 * l.l[i] + 1)};
+    out[2] = {oup(i, oup(i, l)), 4.0 * z * z};
+    return 3;
+  case OP_RD:  // x_j d/dx_i : raise j first, then lower i (clamped)
+    out[0] = {odn(i, oup(j, l)), (double)l.l[i]};
+    out[1] = {oup(i, oup(j, l)), -2.0 * z};
+    return 2;
+  case OP_R:
+    out[0] = {oup(j, l), 1.0};
+    return 1;
+  default:  // OP_CORE
+    out[0] = {oup(i, l), 2.0 * z};
+    return 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Shared building blocks (executed by `nthr` cooperating threads, rank `t`).
+// ---------------------------------------------------------------------------
+__device__ inline double block_elem(const TaskDev &T, const double *block,
+                                    const int sa, const int sb) {
+  return T.transpose ? block[(T.sgfb + sb) * T.nsgfa + T.sgfa + sa]
+                     : block[(T.sgfa + sa) * T.nsgfb + T.sgfb + sb];
+}
+__device__ inline int block_index(const TaskDev &T, const int sa, const int sb) {
+  return T.transpose ? (T.sgfb + sb) * T.nsgfa + T.sgfa + sa
+                     : (T.sgfa + sa) * T.nsgfb + T.sgfb + sb;
+}
+
+template <typename SyncF>
+__device__ inline void decontract_task(const TaskDev &T, const double *block,
+                                       const double *sphi_pool, double *s_work,
+                                       double *s_raw, const int t,
+                                       const int nthr, SyncF sync) {
+  // raw[jco][ico] = sum_{sa,sb} sphi_b[sb][o2+jco] P(sa,sb) sphi_a[sa][o1+ico]
+  const int na = T.ncoseta, nb = T.ncosetb;
+  const double *sphi_a = sphi_pool + T.sphi_a + T.sgfa * T.maxcoa + T.o1;
+  const double *sphi_b = sphi_pool + T.sphi_b + T.sgfb * T.maxcob + T.o2;
+  for (int q = t; q < T.nsgf_setb * na; q += nthr) {
+    const int sb = q / na, ico = q % na;
+    double acc = 0.0;
+    for (int sa = 0; sa < T.nsgf_seta; sa++)
+      acc += block_elem(T, block, sa, sb) * __ldg(&sphi_a[sa * T.maxcoa + ico]);
+    s_work[q] = acc;
+  }
+  sync();
+  for (int q = t; q < nb * na; q += nthr) {
+    const int jco = q / na, ico = q % na;
+    double acc = 0.0;
+    for (int sb = 0; sb < T.nsgf_setb; sb++)
+      acc += __ldg(&sphi_b[sb * T.maxcob + jco]) * s_work[sb * na + ico];
+    s_raw[q] = acc;
+  }
+  sync();
+}
+
+// alpha[d][la][lb][k] for (x-a)^la (x-b)^lb = sum_k alpha_k (x-p)^k
+template <typename SyncF>
+__device__ inline void make_alpha(const TaskDev &T, const int la_c,
+                                  const int lb_c, double *s_alpha, const int t,
+                                  const int nthr, SyncF sync) {
+  const int lp1 = la_c + lb_c + 1;
+  const int n = 3 * (la_c + 1) * (lb_c + 1);
+  for (int q = t; q < n; q += nthr) {
+    const int lb = q % (lb_c + 1);
+    const int la = (q / (lb_c + 1)) % (la_c + 1);
+    const int d = q / ((lb_c + 1) * (la_c + 1));
+    const double pa = T.rp[d] - T.ra[d];
+    const double pb = T.rp[d] - (T.ra[d] + T.rab[d]);
+    double *al = s_alpha + q * lp1;
+    for (int k = 0; k < lp1; k++)
+      al[k] = 0.0;
+    double pas = 1.0;  // pa^(la-s) built downwards from s = la
+    for (int s = la; s >= 0; s--) {
+      double pbt = 1.0;
+      for (int u = lb; u >= 0; u--) {
+        al[s + u] += c_binom[la][s] * pas * c_binom[lb][u] * pbt;
+        pbt *= pb;
+      }
+      pas *= pa;
+    }
+  }
+  sync();
+}
+#define B200_AL(d, la, lb, k)                                                  \
+  s_alpha[((((d) * (la_c + 1) + (la)) * (lb_c + 1) + (lb)) * lp1) + (k)]
+
+// ---------------------------------------------------------------------------
+// pab_to_coef: one warp per task.
+// ---------------------------------------------------------------------------
+struct CoefDims {
+  int work, raw, cab, alpha, cxyz;  // doubles per warp
+  __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz; }
+};
+
+__global__ void __launch_bounds__(128)
+pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
+                   const CoefDims D) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  double *s_work = smem + (size_t)warp * D.total();
+  double *s_raw = s_work + D.work;
+  double *s_cab = s_raw + D.raw;
+  double *s_alpha = s_cab + D.cab;
+  double *s_cxyz = s_alpha + D.alpha;
+  auto sync = [] { __syncwarp(); };
+
+  FuncDesc F;
+  describe_func(func, F);
+
+  for (int it = blockIdx.x * wpc + warp; it < L.ntasks; it += gridDim.x * wpc) {
+    const int itask = L.task_ids ? L.task_ids[it] : it;
+    const TaskDev &T = L.tasks[itask];
+    const int la_c = T.la_max + F.dla_max, lb_c = T.lb_max + F.dlb_max;
+    const int la_min_c = max(T.la_min + F.dla_min, 0);
+    const int lb_min_c = max(T.lb_min + F.dlb_min, 0);
+    const int lp = la_c + lb_c, lp1 = lp + 1, nc = ncoset(lp);
+    double *out = L.coef + L.coef_offsets[itask];
+    if (T.skip) {
+      for (int c = lane; c < nc; c += 32)
+        out[c] = 0.0;
+      continue;
+    }
+    decontract_task(T, pab + T.block_offset, L.sphi_pool, s_work, s_raw, lane,
+                    32, sync);
+
+    // prepare: cab[idx(b')][idx(a')] += coef * raw[idx(b)][idx(a)]
+    const int n1c = ncoset(la_c), n2c = ncoset(lb_c);
+    for (int q = lane; q < n1c * n2c; q += 32)
+      s_cab[q] = 0.0;
+    __syncwarp();
+    const int a_lo = ncoset(T.la_min - 1), a_hi = ncoset(T.la_max);
+    const int b_lo = ncoset(T.lb_min - 1), b_hi = ncoset(T.lb_max);
+    const int npa = a_hi - a_lo, npb = b_hi - b_lo;
+    for (int q = lane; q < npa * npb; q += 32) {
+      const int ia = a_lo + q % npa, ib = b_lo + q / npa;
+      const double p = s_raw[ib * T.ncoseta + ia];
+      if (func == 100) {
+        s_cab[ib * n1c + ia] = p;  // identity: distinct targets
+      } else {
+        const Orb a = orb_of(ia), b = orb_of(ib);
+        for (int tt = 0; tt < F.nterms; tt++) {
+          OpTerm ta[4], tb[4];
+          const int na_t = op_expand(F.t[tt].a, a, T.zeta, ta);
+          const int nb_t = op_expand(F.t[tt].b, b, T.zetb, tb);
+          for (int x = 0; x < na_t; x++)
+            for (int y = 0; y < nb_t; y++)
+              atomicAdd(&s_cab[oidx(tb[y].o) * n1c + oidx(ta[x].o)],
+                        F.t[tt].c * ta[x].c * tb[y].c * p);
+        }
+      }
+    }
+    __syncwarp();
+
+    make_alpha(T, la_c, lb_c, s_alpha, lane, 32, sync);
+
+    // gather: cxyz[k] = prefactor * sum_{a,b} cab[b][a] ax ay az
+    const double rscale = (T.iatom == T.jatom) ? 1.0 : 2.0;
+    const double pref = rscale * T.prefactor;
+    const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
+    const bool to_cijk = !T.use_ortho;
+    for (int c = lane; c < nc; c += 32) {
+      const Orb k = orb_of(c);
+      double acc = 0.0;
+      for (int ib = cb_lo; ib < n2c; ib++) {
+        const Orb b = orb_of(ib);
+        for (int ia = ca_lo; ia < n1c; ia++) {
+          const Orb a = orb_of(ia);
+          if (k.l[0] <= a.l[0] + b.l[0] && k.l[1] <= a.l[1] + b.l[1] &&
+              k.l[2] <= a.l[2] + b.l[2]) {
+            acc += s_cab[ib * n1c + ia] *
+                   (B200_AL(0, a.l[0], b.l[0], k.l[0]) *
+                    B200_AL(1, a.l[1], b.l[1], k.l[1]) *
+                    B200_AL(2, a.l[2], b.l[2], k.l[2]) * pref);
+          }
+        }
+      }
+      if (to_cijk)
+        s_cxyz[c] = acc;
+      else
+        out[c] = acc;
+    }
+    if (to_cijk) {  // lattice-polynomial basis for the general path
+      __syncwarp();
+      const double *Tm = L.cijk_T[T.level * (kMaxLp + 1) + lp];
+      for (int q = lane; q < nc; q += 32) {
+        double acc = 0.0;
+        for (int c = 0; c < nc; c++)
+          acc += __ldg(&Tm[q * nc + c]) * s_cxyz[c];
+        out[q] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// coef_to_hab: one CTA per atom-pair block.
+// ---------------------------------------------------------------------------
+struct PCtx {
+  const double *cab;
+  int m1;
+  double zeta, zetb;
+  double rab[3];
+};
+__device__ inline double cabv(const PCtx &p, const Orb &a, const Orb &b) {
+  return p.cab[oidx(b) * p.m1 + oidx(a)];
+}
+// what: 0 hab, 1 force a (i), 2 force b (i), 3 virial a (i,j), 4 virial b (i,j)
+__device__ inline double vab_plain(const PCtx &p, const int what, const int i,
+                                   const int j, const Orb &a, const Orb &b) {
+  switch (what) {
+  case 0:
+    return cabv(p, a, b);
+  case 1:
+    return 2.0 * p.zeta * cabv(p, oup(i, a), b) - a.l[i] * cabv(p, odn(i, a), b);
+  case 2:
+    return 2.0 * p.zetb * (cabv(p, oup(i, a), b) - p.rab[i] * cabv(p, a, b)) -
+           b.l[i] * cabv(p, a, odn(i, b));
+  case 3:
+    return 2.0 * p.zeta * cabv(p, oup(i, oup(j, a)), b) -
+           a.l[j] * cabv(p, oup(i, odn(j, a)), b);
+  default:
+    return 2.0 * p.zetb *
+               (cabv(p, oup(i, oup(j, a)), b) -
+                cabv(p, oup(i, a), b) * p.rab[j] -
+                cabv(p, oup(j, a), b) * p.rab[i] +
+                cabv(p, a, b) * p.rab[j] * p.rab[i]) -
+           b.l[j] * cabv(p, a, oup(i, odn(j, b)));
+  }
+}
+__device__ inline double vab_elem(const PCtx &p, const bool tau, const int what,
+                                  const int i, const int j, const Orb &a,
+                                  const Orb &b) {
+  if (!tau)
+    return vab_plain(p, what, i, j, a, b);
+  double s = 0.0;
+  for (int k = 0; k < 3; k++) {
+    s += 0.5 * a.l[k] * b.l[k] * vab_plain(p, what, i, j, odn(k, a), odn(k, b));
+    s -= p.zeta * b.l[k] * vab_plain(p, what, i, j, oup(k, a), odn(k, b));
+    s -= a.l[k] * p.zetb * vab_plain(p, what, i, j, odn(k, a), oup(k, b));
+    s += 2.0 * p.zeta * p.zetb * vab_plain(p, what, i, j, oup(k, a), oup(k, b));
+  }
+  return s;
+}
+
+struct HabDims {
+  int work, raw, cab, alpha, cxyz, h, block;  // doubles
+  __host__ __device__ int total() const { return work + raw + cab + alpha + 2 * cxyz + h + block; }
+};
+
+constexpr int kHabThreads = 128;
+
+__global__ void __launch_bounds__(kHabThreads)
+coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int dla_max,
+                   const int dla_min, const int dlb_max, const int dlb_min,
+                   const bool block_in_smem) {
+  extern __shared__ double smem[];
+  double *s_work = smem;
+  double *s_raw = s_work + D.work;
+  double *s_cab = s_raw + D.raw;
+  double *s_alpha = s_cab + D.cab;
+  double *s_cxyz = s_alpha + D.alpha;
+  double *s_cijk = s_cxyz + D.cxyz;
+  double *s_h = s_cijk + D.cxyz;
+  double *s_block = s_h + D.h;
+  __shared__ double s_red[kHabThreads / 32][15];
+  const int t = threadIdx.x;
+  auto sync = [] { __syncthreads(); };
+
+  const int iblock = blockIdx.x;
+  const int first = L.block_first[iblock], last = L.block_first[iblock + 1];
+  if (first >= last)
+    return;
+  const bool do_f = (L.forces != nullptr), do_v = (L.virial != nullptr);
+  double facc[15];  // force a (3), force b (3), virial a+b (9)
+  for (int i = 0; i < 15; i++)
+    facc[i] = 0.0;
+
+  const TaskDev &T0 = L.tasks[L.block_task_ids[first]];
+  const int blk_size = T0.nsgfa * T0.nsgfb;
+  double *g_block = L.hab + T0.block_offset;
+  if (block_in_smem) {
+    for (int q = t; q < blk_size; q += kHabThreads)
+      s_block[q] = 0.0;
+  }
+  __syncthreads();
+
+  for (int it = first; it < last; it++) {
+    const int itask = L.block_task_ids[it];
+    const TaskDev &T = L.tasks[itask];
+    if (T.skip)
+      continue;
+    const int la_c = T.la_max + dla_max, lb_c = T.lb_max + dlb_max;
+    const int la_min_c = max(T.la_min + dla_min, 0);
+    const int lb_min_c = max(T.lb_min + dlb_min, 0);
+    const int lp = la_c + lb_c, lp1 = lp + 1, nc = ncoset(lp);
+    const double *in = L.coef + L.coef_offsets[itask];
+
+    // (1) coefficients, back to the Cartesian polynomial basis if needed
+    if (T.use_ortho) {
+      for (int c = t; c < nc; c += kHabThreads)
+        s_cxyz[c] = in[c];
+    } else {
+      for (int c = t; c < nc; c += kHabThreads)
+        s_cijk[c] = in[c];
+      __syncthreads();
+      const double *Tm = L.cijk_T[T.level * (kMaxLp + 1) + lp];
+      for (int c = t; c < nc; c += kHabThreads) {
+        double acc = 0.0;
+        for (int q = 0; q < nc; q++)
+          acc += __ldg(&Tm[q * nc + c]) * s_cijk[q];
+        s_cxyz[c] = acc;
+      }
+    }
+    make_alpha(T, la_c, lb_c, s_alpha, t, kHabThreads, sync);  // syncs
+
+    // (2) cab[b][a] = prefactor * sum_k cxyz[k] ax ay az
+    const int n1c = ncoset(la_c), n2c = ncoset(lb_c);
+    const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
+    for (int q = t; q < n1c * n2c; q += kHabThreads) {
+      const int ia = q % n1c, ib = q / n1c;
+      double acc = 0.0;
+      if (ia >= ca_lo && ib >= cb_lo) {
+        const Orb a = orb_of(ia), b = orb_of(ib);
+        for (int kz = 0; kz <= a.l[2] + b.l[2]; kz++)
+          for (int ky = 0; ky <= a.l[1] + b.l[1]; ky++)
+            for (int kx = 0; kx <= a.l[0] + b.l[0]; kx++)
+              acc += s_cxyz[coset(kx, ky, kz)] *
+                     (B200_AL(0, a.l[0], b.l[0], kx) *
+                      B200_AL(1, a.l[1], b.l[1], ky) *
+                      B200_AL(2, a.l[2], b.l[2], kz) * T.prefactor);
+      }
+      s_cab[q] = acc;
+    }
+    // (3) density sub-block for forces / virial
+    if (do_f || do_v)
+      decontract_task(T, L.pab + T.block_offset, L.sphi_pool, s_work, s_raw, t,
+                      kHabThreads, sync);
+    __syncthreads();
+
+    // (4) matrix elements for the original l-range
+    PCtx P;
+    P.cab = s_cab, P.m1 = n1c, P.zeta = T.zeta, P.zetb = T.zetb;
+    P.rab[0] = T.rab[0], P.rab[1] = T.rab[1], P.rab[2] = T.rab[2];
+    const int na = T.ncoseta, nb = T.ncosetb;
+    const int a_lo = ncoset(T.la_min - 1), b_lo = ncoset(T.lb_min - 1);
+    for (int q = t; q < na * nb; q += kHabThreads) {
+      const int ia = q % na, ib = q / na;
+      double hval = 0.0;
+      if (ia >= a_lo && ib >= b_lo) {
+        const Orb a = orb_of(ia), b = orb_of(ib);
+        hval = vab_elem(P, L.compute_tau, 0, 0, 0, a, b);
+        if (do_f) {
+          const double pv = s_raw[ib * na + ia];
+          for (int i = 0; i < 3; i++) {
+            facc[i] += pv * vab_elem(P, L.compute_tau, 1, i, 0, a, b);
+            facc[3 + i] += pv * vab_elem(P, L.compute_tau, 2, i, 0, a, b);
+          }
+          if (do_v)
+            for (int i = 0; i < 3; i++)
+              for (int j = 0; j < 3; j++)
+                facc[6 + 3 * i + j] +=
+                    pv * (vab_elem(P, L.compute_tau, 3, i, j, a, b) +
+                          vab_elem(P, L.compute_tau, 4, i, j, a, b));
+        }
+      }
+      s_h[q] = hval;
+    }
+    __syncthreads();
+
+    // (5) contract into the spherical block: block += sphi_a h sphi_b^T
+    const double *sphi_a = L.sphi_pool + T.sphi_a + T.sgfa * T.maxcoa + T.o1;
+    const double *sphi_b = L.sphi_pool + T.sphi_b + T.sgfb * T.maxcob + T.o2;
+    for (int q = t; q < T.nsgf_setb * na; q += kHabThreads) {
+      const int sb = q / na, ico = q % na;
+      double acc = 0.0;
+      for (int jco = 0; jco < nb; jco++)
+        acc += __ldg(&sphi_b[sb * T.maxcob + jco]) * s_h[jco * na + ico];
+      s_work[q] = acc;
+    }
+    __syncthreads();
+    for (int q = t; q < T.nsgf_seta * T.nsgf_setb; q += kHabThreads) {
+      const int sa = q % T.nsgf_seta, sb = q / T.nsgf_seta;
+      double acc = 0.0;
+      for (int ico = 0; ico < na; ico++)
+        acc += s_work[sb * na + ico] * __ldg(&sphi_a[sa * T.maxcoa + ico]);
+      const int ix = block_index(T, sa, sb);
+      if (block_in_smem)
+        s_block[ix] += acc;
+      else
+        atomicAdd(&g_block[ix], acc);
+    }
+    __syncthreads();
+  }
+
+  if (block_in_smem) {
+    // atomics keep aliased block offsets (src/grid/grid_replay.c:175-176) safe
+    for (int q = t; q < blk_size; q += kHabThreads)
+      if (s_block[q] != 0.0)
+        atomicAdd(&g_block[q], s_block[q]);
+  }
+
+  if (do_f) {
+    const int nred = do_v ? 15 : 6;
+    const int lane = t & 31, warp = t >> 5;
+    for (int i = 0; i < nred; i++) {
+      double v = facc[i];
+      for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0)
+        s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (t < nred) {
+      double v = 0.0;
+      for (int w = 0; w < kHabThreads / 32; w++)
+        v += s_red[w][t];
+      const double scale = (T0.iatom == T0.jatom) ? 1.0 : 2.0;
+      if (t < 3)
+        atomicAdd(&L.forces[3 * T0.iatom + t], scale * v);
+      else if (t < 6)
+        atomicAdd(&L.forces[3 * T0.jatom + t - 3], scale * v);
+      else
+        atomicAdd(&L.virial[t - 6], scale * v);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+constexpr size_t kSmemBudget = 200 * 1024;
+
+inline void launch_pab_to_coef(const CoefLaunch &L, const int func, const double *pab,
+                               const int max_nsgf_set, const int max_ncoset_raw,
+                               const int max_la_c, const int max_lb_c) {
+  if (L.ntasks == 0)
+    return;
+  CoefDims D;
+  D.work = max_nsgf_set * max_ncoset_raw;
+  D.raw = max_ncoset_raw * max_ncoset_raw;
+  D.cab = ncoset(max_la_c) * ncoset(max_lb_c);
+  D.alpha = 3 * (max_la_c + 1) * (max_lb_c + 1) * (max_la_c + max_lb_c + 1);
+  D.cxyz = ncoset(max_la_c + max_lb_c);
+  const size_t per_warp = (size_t)D.total() * sizeof(double);
+  B200_ASSERT(per_warp <= kSmemBudget, "basis too large for the coefficient kernel");
+  const int wpc = (int)std::min<size_t>(4, kSmemBudget / per_warp);
+  const size_t bytes = per_warp * wpc;
+  B200_CHECK(cudaFuncSetAttribute(pab_to_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)bytes));
+  const int grid = std::min((L.ntasks + wpc - 1) / wpc, 148 * 16);
+  pab_to_coef_kernel<<<grid, 32 * wpc, bytes, L.stream>>>(L, func, pab, D);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+inline void launch_coef_to_hab(const HabLaunch &L, const int max_ncoset_raw,
+                               const int max_block_size, const int dla_max, const int dla_min,
+                               const int dlb_max, const int dlb_min) {
+  if (L.nblocks == 0)
+    return;
+  HabDims D;
+  D.work = L.max_nsgf_set * max_ncoset_raw;
+  D.raw = max_ncoset_raw * max_ncoset_raw;
+  D.cab = ncoset(L.max_la_l) * ncoset(L.max_lb_l);
+  D.alpha = 3 * (L.max_la_l + 1) * (L.max_lb_l + 1) * (L.max_la_l + L.max_lb_l + 1);
+  D.cxyz = ncoset(L.max_la_l + L.max_lb_l);
+  D.h = max_ncoset_raw * max_ncoset_raw;
+  D.block = max_block_size;
+  bool block_in_smem = true;
+  if ((size_t)D.total() * sizeof(double) > kSmemBudget) {
+    D.block = 0;
+    block_in_smem = false;
+  }
+  const size_t bytes = (size_t)D.total() * sizeof(double);
+  B200_ASSERT(bytes <= kSmemBudget, "basis too large for the hab kernel");
+  B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)bytes));
+  coef_to_hab_kernel<<<L.nblocks, kHabThreads, bytes, L.stream>>>(L, D, dla_max, dla_min, dlb_max,
+                                                                  dlb_min, block_in_smem);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+}  // namespace b200

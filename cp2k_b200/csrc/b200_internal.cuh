@@ -1,0 +1,152 @@
+// Internal declarations of the B200 grid backend (sm_100a only).
+//
+// Data layout in HBM:
+//   TaskDev tasks[ntasks]       one record per Gaussian product, sorted by
+//                               (level, block, iset, jset) like the reference
+//                               (src/grid/ref/grid_ref_task_list.c:26-37,140)
+//   double  coef[sum ncoset(lp)] per-task polynomial coefficients C_xyz in coset
+//                               order (compact: only lx+ly+lz <= lp)
+//   double  sphi_pool[]         all kinds' sphi matrices back to back
+//   grids / pab / hab           caller buffers or backend-owned mirrors
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/grid_b200.h"
+
+#define B200_CHECK(cmd)                                                        \
+  do {                                                                         \
+    cudaError_t e_ = (cmd);                                                    \
+    if (e_ != cudaSuccess) {                                                   \
+      fprintf(stderr, "grid_b200: CUDA error %s at %s:%d\n",                   \
+              cudaGetErrorString(e_), __FILE__, __LINE__);                     \
+      abort();                                                                 \
+    }                                                                          \
+  } while (0)
+
+#define B200_ASSERT(cond, msg)                                                 \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      fprintf(stderr, "grid_b200: %s (%s) at %s:%d\n", msg, #cond, __FILE__,   \
+              __LINE__);                                                       \
+      abort();                                                                 \
+    }                                                                          \
+  } while (0)
+
+namespace b200 {
+
+constexpr int kMaxLSide = 8;   // max angular momentum per side after ldiffs
+constexpr int kMaxLp = 16;     // max la+lb after ldiffs
+constexpr int kNumOrb = 165;   // ncoset(kMaxLSide)
+
+__host__ __device__ inline int ncoset(const int l) {
+  return (l < 0) ? 0 : ((l + 1) * (l + 2) * (l + 3)) / 6;
+}
+__host__ __device__ inline int coset(const int lx, const int ly, const int lz) {
+  const int l = lx + ly + lz;
+  return ncoset(l - 1) + ((l - lx) * (l - lx + 1)) / 2 + lz;
+}
+__host__ __device__ inline int pmod(const int a, const int m) {
+  return ((a % m) + m) % m;
+}
+
+// Per grid level (src/grid/ref/grid_ref_task_list_internal.h:38-46).
+struct LevelDev {
+  int npts_global[3];
+  int npts_local[3];
+  int shift_local[3];
+  int border_width[3];
+  double dh[9];      // dh[i*3+j]: j-th Cartesian component of lattice step i
+  double dh_inv[9];
+};
+
+// One Gaussian product.  Everything that does not depend on `func` is
+// precomputed on the host once per task list.
+struct TaskDev {
+  double ra[3], rab[3], rp[3];
+  double zeta, zetb, zetp;
+  double prefactor;  // exp(-zeta*zetb/zetp*|rab|^2), without rscale
+  double radius;
+  // orthorhombic geometry (src/grid/ref/grid_ref_collint.h:222-254)
+  double roffset[3];
+  double disr_radius;
+  int cubecenter[3];
+  int lb_cube[3];
+  // general geometry (src/grid/ref/grid_ref_collint.h:611-640)
+  double gp[3];
+  int index_min[3], index_max[3];
+  int level, border_mask;
+  int la_max, la_min, lb_max, lb_min;
+  int iatom, jatom;
+  int block_num, block_offset;
+  int iset, jset;
+  int sgfa, sgfb, nsgf_seta, nsgf_setb, nsgfa, nsgfb;
+  int ncoseta, ncosetb;        // ncoset(la_max), ncoset(lb_max)
+  int ncoa, ncob;              // npgf * ncoset: Cartesian size of the set
+  int o1, o2;                  // (ipgf-1)*ncoseta, (jpgf-1)*ncosetb
+  int sphi_a, sphi_b;          // offsets of the kinds' sphi in sphi_pool
+  int maxcoa, maxcob;
+  int transpose;               // iatom <= jatom
+  int use_ortho;               // orthorhombic && border_mask == 0
+  int skip;                    // 2*radius < max|dh|  (collint.h:929-937)
+};
+
+// (lx,ly,lz) of coset index c, for c < ncoset(kMaxLp) -- filled at load time.
+struct OrbTable {
+  unsigned char l[816][3];  // ncoset(15) = 816
+};
+
+// ---- launch bookkeeping ---------------------------------------------------
+void count_launch(int n = 1);
+
+// ---- kernels: coefficients (b200_coef.cu) ----------------------------------
+struct CoefLaunch {
+  const TaskDev *tasks;
+  const int *task_ids;     // nullptr = identity
+  int ntasks;
+  const double *sphi_pool;
+  const int *coef_offsets; // per task (indexed by task id)
+  double *coef;
+  const double *const *cijk_T;  // per (level*(kMaxLp+1)+lp) transform or null
+  cudaStream_t stream;
+};
+
+struct HabLaunch {
+  const TaskDev *tasks;
+  const int *block_task_ids;    // tasks sorted by (block, iset, jset)
+  const int *block_first;       // [nblocks+1] ranges into block_task_ids
+  int nblocks;
+  const double *sphi_pool;
+  const int *coef_offsets;
+  const double *coef;
+  const double *const *cijk_T;
+  const double *pab;            // may be null
+  double *hab;
+  double *forces;               // device [natoms][3] or null
+  double *virial;               // device [9] or null
+  bool compute_tau;
+  int maxco;
+  int max_nsgf_set;
+  int max_la_l, max_lb_l;       // after process ldiffs
+  cudaStream_t stream;
+};
+
+// ---- kernels: generic per-task collocate / integrate (b200_generic.cu) ----
+struct GridLaunch {
+  const TaskDev *tasks;
+  const int *task_ids;     // tasks of this level handled by this kernel
+  int ntasks;
+  LevelDev level;
+  int dl;                  // lp growth for this call
+  const int *coef_offsets;
+  double *coef;            // read (collocate) or written (integrate)
+  double *grid;
+  int max_lp;              // over these tasks, including dl
+  int max_w;               // max cube/box edge over these tasks
+  cudaStream_t stream;
+};
+
+}  // namespace b200

@@ -1,0 +1,128 @@
+/*
+ * grid_b200.h -- C ABI of the B200-native backend for CP2K's grid library.
+ *
+ * Drop-in boundary.  The four task-list entry points have exactly the shape
+ * every backend of the reference exports to its dispatcher, so that
+ * src/grid/grid_task_list.c can select this backend with one more `case` per
+ * switch (see INTEGRATION.md for the patch):
+ *
+ *   grid_b200_create_task_list     replaces  grid_gpu_create_task_list
+ *                                  (src/grid/gpu/grid_gpu_task_list.h:25-38,
+ *                                   called at src/grid/grid_task_list.c:116-124)
+ *   grid_b200_free_task_list       replaces  grid_gpu_free_task_list   (:42, .c:159-164)
+ *   grid_b200_collocate_task_list  replaces  grid_gpu_collocate_task_list
+ *                                  (:48-52, called at .c:215-218)
+ *   grid_b200_integrate_task_list  replaces  grid_gpu_integrate_task_list
+ *                                  (:58-64, called at .c:327-331); `natoms` is
+ *                                  passed like the REF/CPU backends do
+ *                                  (src/grid/ref/grid_ref_task_list.h) so the
+ *                                  forces array can be bounds-checked.
+ *
+ * Semantics are those of the public API (src/grid/grid_task_list.h:19-126):
+ * task indices 1-based, block_offsets 0-based; collocate OVERWRITES every
+ * level's grid; integrate OVERWRITES hab_blocks (all `size` bytes),
+ * forces[natoms][3] and virial[3][3]; forces/virial may be NULL; a non-NULL
+ * *task_list handle is reused.  All functions are void: failures print to
+ * stderr and abort(), as in the reference.  Plain pointers and sizes only.
+ */
+#ifndef GRID_B200_H
+#define GRID_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Layout-compatible with grid_basis_set (src/grid/common/grid_basis_set.h:14-26). */
+typedef struct {
+  int nset;
+  int nsgf;
+  int maxco;
+  int maxpgf;
+  int *lmin;
+  int *lmax;
+  int *npgf;
+  int *nsgf_set;
+  int *first_sgf;
+  double *sphi;
+  double *zet;
+} grid_b200_basis_set;
+
+/* Layout-compatible with offload_buffer (src/offload/offload_buffer.h:16-20).
+ * host_buffer is the source/sink of truth at the call boundary unless
+ * grid_b200_set_device_resident(true) was called AND device_buffer != NULL. */
+typedef struct {
+  size_t size; /* bytes */
+  double *host_buffer;
+  double *device_buffer;
+} grid_b200_buffer;
+
+typedef void grid_b200_task_list;
+
+void grid_b200_create_task_list(
+    const bool orthorhombic, const int ntasks, const int nlevels,
+    const int natoms, const int nkinds, const int nblocks,
+    const int *block_offsets, const double *atom_positions,
+    const int *atom_kinds, const grid_b200_basis_set **basis_sets,
+    const int *level_list, const int *iatom_list, const int *jatom_list,
+    const int *iset_list, const int *jset_list, const int *ipgf_list,
+    const int *jpgf_list, const int *border_mask_list,
+    const int *block_num_list, const double *radius_list,
+    const double *rab_list, const int *npts_global, const int *npts_local,
+    const int *shift_local, const int *border_width, const double *dh,
+    const double *dh_inv, grid_b200_task_list **task_list);
+
+void grid_b200_free_task_list(grid_b200_task_list *task_list);
+
+/* func: enum grid_func (src/grid/common/grid_constants.h:10-46). */
+void grid_b200_collocate_task_list(const grid_b200_task_list *task_list,
+                                   const int func, const int nlevels,
+                                   const grid_b200_buffer *pab_blocks,
+                                   grid_b200_buffer **grids);
+
+void grid_b200_integrate_task_list(const grid_b200_task_list *task_list,
+                                   const bool compute_tau, const int natoms,
+                                   const int nlevels,
+                                   const grid_b200_buffer *pab_blocks,
+                                   const grid_b200_buffer **grids,
+                                   grid_b200_buffer *hab_blocks, double *forces,
+                                   double *virial);
+
+/* ---- backend controls (no counterpart in the reference) ------------------ */
+
+/* Device selection follows offload_get_chosen_device()
+ * (src/offload/offload_library.c); stand-alone it is set explicitly.
+ * Negative = keep the CUDA current device. */
+void grid_b200_set_device(const int device);
+int grid_b200_device_count(void);
+
+/* CUDA stream (cudaStream_t) all work of subsequent calls is enqueued on. */
+void grid_b200_set_stream(void *cuda_stream);
+
+/* true: a non-NULL device_buffer is authoritative on entry and exit (no
+ * host<->device copies inside the call, the call returns after enqueueing).
+ * false (default): host_buffer is authoritative; copies are part of the call. */
+void grid_b200_set_device_resident(const bool flag);
+
+/* 0 = automatic (tiled kernels where applicable), 1 = force the generic
+ * per-task kernels everywhere (used by the parity tests to cover both). */
+void grid_b200_set_kernel_variant(const int variant);
+
+/* Number of CUDA kernels launched by this library since load. */
+long long grid_b200_get_launch_count(void);
+
+/* Workload statistics of a task list (model flop counts per SURVEY.md 8(d)).
+ * Fills at most n doubles, returns how many were written:
+ *  [0] ntasks [1] tasks on the tiled path [2] tasks on the generic path
+ *  [3] (task,tile) pairs [4] grid points visited per pass (REF bounds)
+ *  [5] model flops of collocate(AB) [6] model flops of integrate (no forces)
+ *  [7] max lp [8] max cube half-width [9] nlevels [10] nblocks */
+int grid_b200_get_stats(const grid_b200_task_list *task_list, double *out,
+                        const int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRID_B200_H */

@@ -688,7 +688,7 @@ static bool cab_grid(const int dir, const bool ortho, const int border_mask,
   const double t2 = 0.5 * (lp + 1) * (lp + 2);
   if (use_ortho)
     g_cnt.flops += pts * (2.0 * (lp + 1) + (dir > 0 ? 1 : 0)) +
-                   rows * 4.0 * t2 + planes * 2.0 * ncoset(lp);
+                   rows * 2.0 * t2 + planes * 2.0 * ncoset(lp);
   else
     g_cnt.flops += pts * (3.0 * (lp + 1) + (dir > 0 ? 4 : 3)) +
                    rows * (2.0 * t2 + (lp + 1) + 40.0) +
