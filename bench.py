@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the grid hot path: one "step" = one SCF iteration's worth of
+grid work = grid_collocate_task_list(GRID_FUNC_AB) + grid_integrate_task_list
+on the synthetic-but-faithful H2O-N task list (cp2k_b200/workload.py).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--workload H2O-256] [--forces]
+
+Prints ONE JSON line (rank 0).  `value` is model GFLOP/s (algorithmic FP64 flops
+of the reference loop nest, SURVEY.md 8(d), divided by the device time of the
+step, max over ranks) with everything resident in HBM; `e2e` is the same metric
+through the public API with HOST buffers (H2D/D2H inside the timed region);
+`ms_per_step` is the seconds-per-SCF-step half of BASELINE.json's metric.
+Multi-GPU (strong scaling): the matrix blocks -- and with them the tasks -- are
+split over the ranks, every rank collocates onto replicated grids which are
+summed with one NCCL all-reduce (the reference's replicated-level mode,
+src/pw/realspace_grid_types.F:763-825); integrate needs no exchange.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_PEAK_TFLOPS = 36.1  # measured on this pool's B200 (profiles/microbench/mb.log, DFMA loop)
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {"hbm_gbs": 6650.0, "_fallback": True}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in out.strip().split(",")]
+                if len(p) >= 6:
+                    self.samples.append(p)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def split_blocks(wl, world, rank):
+    """Cost-balanced assignment of matrix blocks (atom pairs) to ranks; a task
+    follows its block (cf. load_balance_replicated, src/task_list_methods.F:1611)."""
+    if world == 1:
+        return wl
+    import heapq
+
+    t = wl.tasks
+    cost = (t["radius_list"] / np.array([np.linalg.norm(wl.layouts[l - 1].dh[0]) for l in t["level_list"]])) ** 3
+    bcost = np.bincount(t["block_num_list"] - 1, weights=cost, minlength=wl.nblocks)
+    owner = np.zeros(wl.nblocks, dtype=np.int32)
+    heap = [(0.0, r) for r in range(world)]
+    for b in np.argsort(-bcost):
+        load, r = heapq.heappop(heap)
+        owner[b] = r
+        heapq.heappush(heap, (load + bcost[b], r))
+    return wl.subset(owner[t["block_num_list"] - 1] == rank)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU backend (GRID_BACKEND_CPU, OpenMP on
+    all host cores) from oracle/_ref, same workload, metric and unit."""
+    from cp2k_b200.grid_api import GRID_BACKEND_CPU, OffloadBuffer
+    from cp2k_b200.workload import build_h2o_workload
+    from oracle import pyref
+
+    if not pyref.have_reference():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgrid_ref.so not built"}))
+        return
+    wl = build_h2o_workload(args.workload)
+    res = cpu_reference_timing(wl, args.steps, args.warmup, args.forces, budget_s=args.cpu_budget)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(wl, args, extra={"sample": res["sample"]}),
+        "cpu_baseline": {"value": res["value"], "unit": "GFLOP/s", "cores": res["cores"], "kind": "reference",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+METRIC = "grid collocate+integrate model FP64 GFLOP/s per SCF step (s/SCF-step = ms_per_step/1000)"
+
+
+def bench_config(wl, args, extra=None):
+    cfg = {"workload": f"{args.workload} GPW {wl.meta['basis']} cutoff 280 Ry rel_cutoff 30 Ry 4 levels "
+                       f"{wl.meta['npts']}; step = collocate(GRID_FUNC_AB) + integrate"
+                       + ("+forces+virial" if args.forces else ""),
+           "ntasks": wl.ntasks, "nblocks": wl.nblocks, "natoms": wl.natoms,
+           "l2": "per-step working set (task records + P/H blocks + grids > 0.5 GB) exceeds the 126 MB L2",
+           "parallelism": f"blocks/tasks split over {args.gpus} GPU(s), replicated grids, NCCL all-reduce"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0):
+    """Times the unmodified reference CPU backend on a bounded sample of `wl`."""
+    from cp2k_b200.grid_api import GRID_BACKEND_CPU, OffloadBuffer
+    from oracle import pyref
+
+    lib = pyref.load_reference(GRID_BACKEND_CPU)
+    ora = pyref.load_oracle()
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(7)
+
+    def one(sample_wl, nsteps, nwarm):
+        tl = sample_wl.create(lib)
+        pab = sample_wl.random_pab(1)
+        grids = sample_wl.new_grids()
+        hab = OffloadBuffer(sample_wl.pab_len)
+        f = np.zeros((sample_wl.natoms, 3)) if forces else None
+        v = np.zeros((3, 3)) if forces else None
+        times = []
+        for i in range(nwarm + nsteps):
+            t0 = time.perf_counter()
+            tl.collocate(100, pab, grids)
+            tl.integrate(False, pab if forces else None, grids, hab, f, v)
+            dt = time.perf_counter() - t0
+            if i >= nwarm:
+                times.append(dt)
+        tl.free()
+        return float(np.mean(times))
+
+    # calibrate on 1/16 of the blocks, then take the largest sample that fits the budget
+    nb = wl.nblocks
+    probe = wl.subset(((wl.tasks["block_num_list"] - 1) % 16) == 0)
+    t_probe = one(probe, 1, 1)
+    per_task = t_probe / max(probe.ntasks, 1)
+    full_est = per_task * wl.ntasks
+    total_steps = steps + warmup
+    frac = min(1.0, budget_s / max(full_est * total_steps, 1e-9))
+    if frac >= 0.999:
+        sample, desc = wl, f"full task list ({wl.ntasks} tasks)"
+    else:
+        stride = int(np.ceil(1.0 / frac))
+        sample = wl.subset(((wl.tasks["block_num_list"] - 1) % stride) == 0)
+        desc = f"every {stride}-th matrix block ({sample.ntasks} of {wl.ntasks} tasks), full-size grids"
+    t_step = one(sample, steps, warmup)
+    flops = model_flops_cpu(sample, ora)
+    return {"value": flops / t_step * 1e-9, "ms_per_step": t_step * 1e3, "cores": cores, "sample": desc,
+            "sample_fraction": sample.ntasks / wl.ntasks}
+
+
+def model_flops_cpu(wl, ora):
+    """Model flops of collocate + integrate (no GPU needed): walks the REF bounds
+    with the oracle's counters on a thinned task list and scales up."""
+    # the GPU path gets exact counts from the backend; here a 1/64 sample is enough
+    n = wl.ntasks
+    stride = max(1, n // 20000)
+    sub = wl.subset(np.arange(0, n, stride))
+    from cp2k_b200.grid_api import OffloadBuffer
+
+    tl = sub.create(ora)
+    ora.reset_counters()
+    pab = sub.random_pab(1)
+    grids = sub.new_grids()
+    tl.collocate(100, pab, grids)
+    c = ora.counters()
+    tl.free()
+    # integrate costs one flop per point less than collocate
+    coll = c["flops"]
+    integ = c["flops"] - c["npts"]
+    return (coll + integ) * (n / sub.ntasks)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="H2O-256")
+    ap.add_argument("--forces", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from cp2k_b200 import OffloadBuffer, load_b200
+    from cp2k_b200.workload import build_h2o_workload
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = load_b200()
+    lib.set_device(local_rank)
+    lib.set_kernel_variant(args.variant)
+
+    wl_full = build_h2o_workload(args.workload)
+    wl = split_blocks(wl_full, world, rank)
+    tl = wl.create(lib)
+    st = lib.stats(tl)
+    flops_local = st["flops_collocate"] + st["flops_integrate"]
+    flops_t = torch.tensor([flops_local, st["flops_collocate"], st["flops_integrate"], st["npts_model"]],
+                           dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(flops_t)
+    flops_total, flops_coll, flops_int, npts_total = (float(x) for x in flops_t.cpu())
+
+    # ---- resident-in-HBM arm -------------------------------------------------
+    pab_h = wl.random_pab(1)
+    pab = OffloadBuffer.with_device(wl.pab_len)
+    pab.device.copy_(torch.from_numpy(pab_h.host))
+    pab.host[:] = pab_h.host
+    grids = [OffloadBuffer.with_device(l.npts_local_total) for l in wl.layouts]
+    hab = OffloadBuffer.with_device(wl.pab_len)
+    forces = np.zeros((wl.natoms, 3)) if args.forces else None
+    virial = np.zeros((3, 3)) if args.forces else None
+
+    def step_resident():
+        tl.collocate(100, pab, grids)
+        if world > 1:
+            for g in grids:
+                dist.all_reduce(g.device)
+        tl.integrate(False, pab if args.forces else None, grids, hab, forces, virial)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib.set_device_resident(True)
+    launches0 = lib.launch_count()
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    launches_per_step = (lib.launch_count() - launches0) // max(args.warmup, 1) if args.warmup else None
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    launches = lib.launch_count() - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    clocks = sampler.finish() if rank == 0 else None
+
+    # ---- per-kernel roofline (device events inside the library) ---------------
+    lib.set_timing(True)
+    lib.timings()
+    for _ in range(args.steps):
+        step_resident()
+    barrier()
+    tm = lib.timings()
+    lib.set_timing(False)
+    peaks = load_peaks()
+    coll_ms = tm["collocate"][0] / args.steps
+    int_ms = tm["integrate"][0] / args.steps
+    dom = "collocate" if coll_ms >= int_ms else "integrate"
+    dom_ms = max(coll_ms, int_ms)
+    dom_flops = st["flops_collocate"] if dom == "collocate" else st["flops_integrate"]
+    grid_bytes = 8.0 * sum(l.npts_local_total for l in wl.layouts)
+    alg_bytes = grid_bytes + 8.0 * wl.pab_len + 72.0 * wl.ntasks
+    achieved_tf = dom_flops / (dom_ms * 1e-3) * 1e-12 if dom_ms > 0 else 0.0
+    roofline = {
+        "bound": "fp64", "kernel": f"{dom} grid kernels (all levels of one call)",
+        "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+        "frac": achieved_tf / FP64_PEAK_TFLOPS, "traffic": None,
+        "peak_source": "measured DFMA loop, profiles/microbench (MEASURED_PEAKS.json has no FP64 entry)",
+        "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (dom_ms * 1e-3) * 1e-9 if dom_ms else 0,
+                "peak_gbs": peaks.get("hbm_gbs"), "of": "fallback" if peaks.get("_fallback") else "measured"},
+        "phase_ms_per_step": {k: v[0] / args.steps for k, v in tm.items()},
+    }
+
+    # ---- end-to-end arm: host buffers through the public API -------------------
+    lib.set_device_resident(False)
+    pab_e = OffloadBuffer(wl.pab_len, pinned=True)
+    pab_e.host[:] = pab_h.host
+    grids_e = [OffloadBuffer.with_device(l.npts_local_total) for l in wl.layouts]
+    hab_e = OffloadBuffer(wl.pab_len, pinned=True)
+
+    def step_e2e():
+        tl.collocate(100, pab_e, grids_e)  # H2D pab, kernels, D2H grids
+        if world > 1:
+            for g in grids_e:
+                dist.all_reduce(g.device)
+                g.host[:] = g.device.cpu().numpy()[: g.host.size]
+        tl.integrate(False, pab_e if args.forces else None, grids_e, hab_e, forces, virial)  # H2D grids, D2H hab
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    n_e2e = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        step_e2e()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_ms = float(dt.item()) / n_e2e * 1e3
+    h2d = 8 * wl.pab_len * (2 if args.forces else 1) + int(grid_bytes)
+    d2h = int(grid_bytes) + 8 * wl.pab_len
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pyref
+
+        if pyref.have_reference():
+            r = cpu_reference_timing(wl_full, 2, 1, args.forces, budget_s=args.cpu_budget)
+            cpu_baseline = {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": "reference",
+                            "sample": r["sample"], "ms_per_step_sample": r["ms_per_step"],
+                            "ms_per_step_extrapolated": r["ms_per_step"] / r["sample_fraction"]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": flops_total / (ms_per_step * 1e-3) * 1e-9, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "s_per_scf_step": ms_per_step * 1e-3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": bench_config(wl_full, args, extra={"model_gflop_per_step": flops_total * 1e-9,
+                                                         "grid_points_per_pass": npts_total}),
+            "clocks": clocks,
+            "e2e": {"value": flops_total / (e2e_ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    tl.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

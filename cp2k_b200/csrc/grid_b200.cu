@@ -37,6 +37,37 @@ static bool g_tables_uploaded[64] = {false};
 
 void count_launch(int n) { g_launches += n; }
 
+// Optional device-side timing of the library's own phases (CUDA events on the
+// launching stream), used by bench.py for the per-kernel roofline numbers.
+enum TimedClass { T_PAB2COEF = 0, T_COLLOCATE, T_INTEGRATE, T_COEF2HAB, T_H2D, T_D2H, T_MEMSET, T_NCLASS };
+struct TimedSpan {
+  cudaEvent_t a, b;
+  int cls;
+};
+static bool g_timing = false;
+static std::vector<TimedSpan> g_spans;
+static double g_ms[T_NCLASS] = {0};
+static double g_nspans[T_NCLASS] = {0};
+struct ScopedTimer {
+  TimedSpan sp;
+  cudaStream_t s;
+  bool on;
+  ScopedTimer(int cls, cudaStream_t stream) : s(stream), on(g_timing) {
+    if (!on)
+      return;
+    sp.cls = cls;
+    B200_CHECK(cudaEventCreate(&sp.a));
+    B200_CHECK(cudaEventCreate(&sp.b));
+    B200_CHECK(cudaEventRecord(sp.a, s));
+  }
+  ~ScopedTimer() {
+    if (!on)
+      return;
+    B200_CHECK(cudaEventRecord(sp.b, s));
+    g_spans.push_back(sp);
+  }
+};
+
 static void activate_device() {
   if (g_device >= 0)
     B200_CHECK(cudaSetDevice(g_device));
@@ -507,6 +538,28 @@ void grid_b200_set_device_resident(const bool flag) { g_device_resident = flag; 
 void grid_b200_set_kernel_variant(const int variant) { g_variant = variant; }
 long long grid_b200_get_launch_count(void) { return g_launches.load(); }
 
+void grid_b200_set_timing(const bool flag) { g_timing = flag; }
+
+int grid_b200_get_timings(double *out, const int n) {
+  for (auto &sp : g_spans) {
+    B200_CHECK(cudaEventSynchronize(sp.b));
+    float ms = 0.f;
+    B200_CHECK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    g_ms[sp.cls] += ms;
+    g_nspans[sp.cls] += 1;
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
+  g_spans.clear();
+  const int m = std::min(n / 2, (int)T_NCLASS);
+  for (int i = 0; i < m; i++) {
+    out[2 * i] = g_ms[i];
+    out[2 * i + 1] = g_nspans[i];
+    g_ms[i] = 0, g_nspans[i] = 0;
+  }
+  return m;
+}
+
 void grid_b200_create_task_list(
     const bool orthorhombic, const int ntasks, const int nlevels, const int natoms,
     const int nkinds, const int nblocks, const int *block_offsets, const double *atom_positions,
@@ -589,8 +642,11 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
       tl.d_pab.ensure(pab_blocks->size / sizeof(double));
       dst = tl.d_pab.p;
     }
-    B200_CHECK(cudaMemcpyAsync(dst, pab_blocks->host_buffer, pab_blocks->size,
-                               cudaMemcpyHostToDevice, s));
+    {
+      ScopedTimer tm(T_H2D, s);
+      B200_CHECK(cudaMemcpyAsync(dst, pab_blocks->host_buffer, pab_blocks->size,
+                                 cudaMemcpyHostToDevice, s));
+    }
     d_pab = dst;
   }
 
@@ -598,8 +654,11 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   CL.tasks = tl.d_tasks.p, CL.task_ids = nullptr, CL.ntasks = tl.ntasks;
   CL.sphi_pool = tl.d_sphi.p, CL.coef_offsets = tl.d_coef_off[dl].p, CL.coef = tl.d_coef.p;
   CL.cijk_T = tl.d_Tptrs.p, CL.stream = s;
-  launch_pab_to_coef(CL, func, d_pab, tl.max_nsgf_set, tl.max_ncoset_raw,
-                     tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
+  {
+    ScopedTimer tm(T_PAB2COEF, s);
+    launch_pab_to_coef(CL, func, d_pab, tl.max_nsgf_set, tl.max_ncoset_raw,
+                       tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
+  }
 
   for (int l = 0; l < nlevels; l++) {
     const LevelDev &L = tl.levels[l];
@@ -612,24 +671,31 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
       tl.d_grids[l].ensure(npts);
       d_grid = tl.d_grids[l].p;
     }
-    B200_CHECK(cudaMemsetAsync(d_grid, 0, npts * sizeof(double), s));
-
+    {
+      ScopedTimer tm(T_MEMSET, s);
+      B200_CHECK(cudaMemsetAsync(d_grid, 0, npts * sizeof(double), s));
+    }
     const bool force_generic = (g_variant == 1);
     GridLaunch GL;
     GL.tasks = tl.d_tasks.p, GL.level = L, GL.dl = dl;
     GL.coef_offsets = tl.d_coef_off[dl].p, GL.coef = tl.d_coef.p, GL.grid = d_grid;
     GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = s;
-    if (force_generic || !tiled_supports(li.tiled, li.max_lp0 + dl)) {
-      GL.task_ids = tl.d_iota.p + li.first, GL.ntasks = li.last - li.first;
-      launch_generic(GL, true);
-    } else {
-      launch_tiled_collocate(li.tiled, GL);
-      GL.task_ids = tl.d_generic_ids.p + tl.generic_first[l], GL.ntasks = li.n_generic;
-      launch_generic(GL, true);
+    {
+      ScopedTimer tm(T_COLLOCATE, s);
+      if (force_generic || !tiled_supports(li.tiled, li.max_lp0 + dl)) {
+        GL.task_ids = tl.d_iota.p + li.first, GL.ntasks = li.last - li.first;
+        launch_generic(GL, true);
+      } else {
+        launch_tiled_collocate(li.tiled, GL);
+        GL.task_ids = tl.d_generic_ids.p + tl.generic_first[l], GL.ntasks = li.n_generic;
+        launch_generic(GL, true);
+      }
     }
-    if (!resident)
+    if (!resident) {
+      ScopedTimer tm(T_D2H, s);
       B200_CHECK(cudaMemcpyAsync(grids[l]->host_buffer, d_grid, npts * sizeof(double),
                                  cudaMemcpyDeviceToHost, s));
+    }
   }
   if (!g_device_resident)
     B200_CHECK(cudaStreamSynchronize(s));
@@ -687,6 +753,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
         tl.d_grids[l].ensure(npts);
         d_grid = tl.d_grids[l].p;
       }
+      ScopedTimer tm(T_H2D, s);
       B200_CHECK(cudaMemcpyAsync(d_grid, grids[l]->host_buffer, npts * sizeof(double),
                                  cudaMemcpyHostToDevice, s));
     }
@@ -695,6 +762,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
     GL.tasks = tl.d_tasks.p, GL.level = L, GL.dl = dl;
     GL.coef_offsets = tl.d_coef_off[dl].p, GL.coef = tl.d_coef.p, GL.grid = d_grid;
     GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = s;
+    ScopedTimer tm(T_INTEGRATE, s);
     if (force_generic || !tiled_supports(li.tiled, li.max_lp0 + dl)) {
       GL.task_ids = tl.d_iota.p + li.first, GL.ntasks = li.last - li.first;
       launch_generic(GL, false);
@@ -715,6 +783,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
         tl.d_pab.ensure(pab_blocks->size / sizeof(double));
         dst = tl.d_pab.p;
       }
+      ScopedTimer tm(T_H2D, s);
       B200_CHECK(cudaMemcpyAsync(dst, pab_blocks->host_buffer, pab_blocks->size,
                                  cudaMemcpyHostToDevice, s));
       d_pab = dst;
@@ -726,9 +795,12 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
     tl.d_hab.ensure(hab_blocks->size / sizeof(double));
     d_hab = tl.d_hab.p;
   }
-  B200_CHECK(cudaMemsetAsync(d_hab, 0, hab_blocks->size, s));
   tl.d_fv.ensure((size_t)3 * natoms + 9);
-  B200_CHECK(cudaMemsetAsync(tl.d_fv.p, 0, ((size_t)3 * natoms + 9) * sizeof(double), s));
+  {
+    ScopedTimer tm(T_MEMSET, s);
+    B200_CHECK(cudaMemsetAsync(d_hab, 0, hab_blocks->size, s));
+    B200_CHECK(cudaMemsetAsync(tl.d_fv.p, 0, ((size_t)3 * natoms + 9) * sizeof(double), s));
+  }
 
   HabLaunch HL;
   HL.tasks = tl.d_tasks.p, HL.block_task_ids = tl.d_block_task_ids.p;
@@ -739,11 +811,15 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   HL.virial = do_v ? tl.d_fv.p + (size_t)3 * natoms : nullptr;
   HL.compute_tau = compute_tau, HL.maxco = tl.maxco, HL.max_nsgf_set = tl.max_nsgf_set;
   HL.max_la_l = tl.max_la + dla_max, HL.max_lb_l = tl.max_lb + dlb_max, HL.stream = s;
-  launch_coef_to_hab(HL, tl.max_ncoset_raw, tl.max_block_size, dla_max, dla_min, dlb_max, dlb_min);
-
-  if (!hab_resident)
+  {
+    ScopedTimer tm(T_COEF2HAB, s);
+    launch_coef_to_hab(HL, tl.max_ncoset_raw, tl.max_block_size, dla_max, dla_min, dlb_max, dlb_min);
+  }
+  if (!hab_resident) {
+    ScopedTimer tm(T_D2H, s);
     B200_CHECK(cudaMemcpyAsync(hab_blocks->host_buffer, d_hab, hab_blocks->size,
                                cudaMemcpyDeviceToHost, s));
+  }
   if (do_f)
     B200_CHECK(cudaMemcpyAsync(forces, tl.d_fv.p, sizeof(double) * 3 * natoms,
                                cudaMemcpyDeviceToHost, s));

@@ -339,6 +339,25 @@ class B200Library(GridLibrary):
         L.grid_b200_set_kernel_variant.restype = None
         L.grid_b200_get_stats.argtypes = [C.c_void_p, _dptr, C.c_int]
         L.grid_b200_get_stats.restype = C.c_int
+        L.grid_b200_set_device.argtypes = [C.c_int]
+        L.grid_b200_set_device.restype = None
+        L.grid_b200_set_timing.argtypes = [C.c_bool]
+        L.grid_b200_set_timing.restype = None
+        L.grid_b200_get_timings.argtypes = [_dptr, C.c_int]
+        L.grid_b200_get_timings.restype = C.c_int
+
+    def set_device(self, device: int) -> None:
+        self.lib.grid_b200_set_device(int(device))
+
+    def set_timing(self, flag: bool) -> None:
+        self.lib.grid_b200_set_timing(bool(flag))
+
+    def timings(self) -> dict:
+        """Drain the device-side phase timers: {phase: (milliseconds, spans)}."""
+        buf = np.zeros(14, dtype=np.float64)
+        n = self.lib.grid_b200_get_timings(_dp(buf), 14)
+        names = ["pab_to_coef", "collocate", "integrate", "coef_to_hab", "h2d", "d2h", "memset"]
+        return {names[i]: (float(buf[2 * i]), int(buf[2 * i + 1])) for i in range(n)}
 
     def set_device_resident(self, flag: bool) -> None:
         """When True, non-NULL ``device_buffer`` members are authoritative at

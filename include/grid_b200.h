@@ -113,6 +113,15 @@ void grid_b200_set_kernel_variant(const int variant);
 /* Number of CUDA kernels launched by this library since load. */
 long long grid_b200_get_launch_count(void);
 
+/* Device-side phase timing (CUDA events on the launching stream) for the
+ * roofline report.  get_timings drains the recorded spans into
+ * out[2*c] = milliseconds, out[2*c+1] = number of spans, for the classes
+ * c = 0 pab->coef, 1 collocate grid kernels, 2 integrate grid kernels,
+ * 3 coef->hab, 4 host->device copies, 5 device->host copies, 6 memsets;
+ * returns the number of classes written (n/2 at most) and resets them. */
+void grid_b200_set_timing(const bool flag);
+int grid_b200_get_timings(double *out, const int n);
+
 /* Workload statistics of a task list (model flop counts per SURVEY.md 8(d)).
  * Fills at most n doubles, returns how many were written:
  *  [0] ntasks [1] tasks on the tiled path [2] tasks on the generic path
