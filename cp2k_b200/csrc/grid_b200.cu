@@ -499,7 +499,7 @@ static void build_task_list(
   for (int l = 0; l < nlevels; l++) {
     LevelInfo &li = tl.linfo[l];
     std::vector<int> generic_ids;
-    build_tiled_level(li.tiled, tl.levels[l], tl.h_tasks, li.first, li.last, generic_ids, s);
+    build_tiled_level(li.tiled, tl.levels[l], tl.h_tasks, tl.d_tasks.p, li.first, li.last, generic_ids, s);
     li.n_generic = (int)generic_ids.size();
     tl.generic_first[l] = (int)tl.h_generic_ids.size();
     tl.h_generic_ids.insert(tl.h_generic_ids.end(), generic_ids.begin(), generic_ids.end());
@@ -662,7 +662,7 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
 
   for (int l = 0; l < nlevels; l++) {
     const LevelDev &L = tl.levels[l];
-    const LevelInfo &li = tl.linfo[l];
+    LevelInfo &li = tl.linfo[l];
     const size_t npts = (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2];
     B200_ASSERT(grids[l]->size >= npts * sizeof(double), "grid buffer smaller than npts_local");
     const bool resident = g_device_resident && use_caller_device(grids[l]);
@@ -741,10 +741,14 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   ensure_coef_offsets(tl, dl, s);
   ensure_transforms(tl, dl, s);
   tl.d_coef.ensure(tl.coef_total[dl]);
+  {  // the tiled integrate kernel accumulates into the coefficients
+    ScopedTimer tm(T_MEMSET, s);
+    B200_CHECK(cudaMemsetAsync(tl.d_coef.p, 0, tl.coef_total[dl] * sizeof(double), s));
+  }
 
   for (int l = 0; l < nlevels; l++) {
     const LevelDev &L = tl.levels[l];
-    const LevelInfo &li = tl.linfo[l];
+    LevelInfo &li = tl.linfo[l];
     const size_t npts = (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2];
     B200_ASSERT(grids[l]->size >= npts * sizeof(double), "grid buffer smaller than npts_local");
     double *d_grid = use_caller_device(grids[l]) ? grids[l]->device_buffer : nullptr;
