@@ -369,7 +369,10 @@ def main():
             "s_per_scf_step": ms_per_step * 1e-3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": bench_config(wl_full, args, extra={"model_gflop_per_step": flops_total * 1e-9,
-                                                         "grid_points_per_pass": npts_total}),
+                                                         "grid_points_per_pass": npts_total,
+                                                         "tasks_tiled": st["ntasks_fast"],
+                                                         "tasks_generic": st["ntasks_generic"],
+                                                         "task_block_pairs": st["npairs"]}),
             "clocks": clocks,
             "e2e": {"value": flops_total / (e2e_ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e},

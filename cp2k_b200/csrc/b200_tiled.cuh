@@ -33,16 +33,23 @@
 #include <cub/device/device_scan.cuh>
 
 #include "b200_generic.cuh"
+#include "b200_pfma.cuh"
 
 namespace b200 {
 
 constexpr int kBX = 8, kBY = 8, kBZ = 16;     // block (warp footprint)
-constexpr int kTiledThreads = 256;            // 8 autonomous warps
+constexpr int kTiledThreads = 128;            // 4 autonomous warps
 constexpr int kTiledWarps = kTiledThreads / 32;
 constexpr int kTiledMaxLp = 6;                // beyond: generic kernels
-constexpr int kTiledMaxN = 60;                // max discretised radius index
+constexpr int kTiledMaxN = 30;                // max discretised radius index (sphere tables <= ~40 KB)
 constexpr int kLpBuckets = kTiledMaxLp + 1;
 constexpr int kItemPairs = 1024;              // pairs per work item (upper bound)
+// lp classes (by lp0 = la_max + lb_max): separate kernel instantiations keep the
+// code of each kernel small (instruction cache!) and the registers low
+constexpr int kNumClasses = 3;
+__host__ __device__ inline int lp_class(const int lp0) { return lp0 <= 2 ? 0 : (lp0 <= 4 ? 1 : 2); }
+constexpr int kClassLo[kNumClasses] = {0, 3, 5};
+constexpr int kClassHi[kNumClasses] = {2, 4, 6};
 
 struct TTask {            // static per-task data of the tiled path
   double roff[3];
@@ -54,17 +61,20 @@ struct TTask {            // static per-task data of the tiled path
 };
 
 struct TPair {            // 8 bytes
-  int ttask;
+  unsigned key;           // ttask (21 bits) | n << 21 (6 bits) | lp0 << 27 (3 bits)
   signed char o[3];       // cube centre relative to the block origin
-  unsigned char lp0;
+  unsigned char pad;
 };
+__host__ __device__ inline int pair_ttask(const TPair &P) { return (int)(P.key & 0x1fffffu); }
+__host__ __device__ inline int pair_n(const TPair &P) { return (int)((P.key >> 21) & 63u); }
+__host__ __device__ inline int pair_lp0(const TPair &P) { return (int)(P.key >> 27); }
 
 struct TWork {
   int x0, y0, z0;         // block origin (local grid indices)
   int first, last;        // pair range
 };
 
-struct KTabHeader {       // per radius index n
+struct alignas(16) KTabHeader {  // per radius index n (read as one int4 on the device)
   int offset;             // into the byte table
   int nbx, nby, nbz;      // -lb per axis
 };
@@ -72,6 +82,13 @@ struct KTabHeader {       // per radius index n
 struct TiledLevel {
   long long npairs = 0;
   int nwork = 0;
+  int class_work_first[kNumClasses + 1] = {0, 0, 0, 0};  // work item ranges per lp class
+  int class_ntasks[kNumClasses] = {0, 0, 0};
+  int class_tt_first[kNumClasses + 1] = {0, 0, 0, 0};       // ttask ranges per lp class
+  std::vector<int> h_tt_task;                                // TaskDev id per ttask (class-sorted)
+  int coef_base[8][kNumClasses] = {};                        // per dl: start of the class's slots
+  int max_nb = 0;
+  int *d_class_task_ids[kNumClasses] = {nullptr, nullptr, nullptr};  // TaskDev ids per class
   int ntasks_tiled = 0;
   int max_lp0 = 0;
   int ktab_bytes = 0;
@@ -87,6 +104,10 @@ struct TiledLevel {
   void release() {
     cudaFree(d_ttasks), cudaFree(d_pairs), cudaFree(d_work), cudaFree(d_khead), cudaFree(d_ktab);
     cudaFree(d_etab);
+    for (auto &p : d_class_task_ids) {
+      cudaFree(p);
+      p = nullptr;
+    }
     for (auto &p : d_tcoef) {
       cudaFree(p);
       p = nullptr;
@@ -104,6 +125,7 @@ struct TiledLevel {
 // ---------------------------------------------------------------------------
 inline void build_ktabs(const LevelDev &L, const int max_n, std::vector<KTabHeader> &heads,
                         std::vector<signed char> &tab) {
+  // Stored by SIGNED cube offsets: K[n][dj + nby][di + nbx], dj in [-nby, nby+1].
   const double h[3] = {L.dh[0], L.dh[4], L.dh[8]};
   const double hinv[3] = {L.dh_inv[0], L.dh_inv[4], L.dh_inv[8]};
   const double drmin = fmin(h[0], fmin(h[1], h[2]));
@@ -131,7 +153,13 @@ inline void build_ktabs(const LevelDev &L, const int max_n, std::vector<KTabHead
           K[(size_t)jd * px + id] = (signed char)std::max<int>(K[(size_t)jd * px + id], kd);
       }
     }
-    tab.insert(tab.end(), K.begin(), K.end());
+    const int wx = 2 * nb[0] + 2, wy = 2 * nb[1] + 2;
+    for (int tj = 0; tj < wy; tj++)
+      for (int ti = 0; ti < wx; ti++) {
+        const int dj = tj - nb[1], di = ti - nb[0];
+        const int mj = (dj <= 0) ? -dj : dj - 1, mi = (di <= 0) ? -di : di - 1;
+        tab.push_back(K[(size_t)mj * px + mi]);
+      }
     heads[n] = H;
   }
 }
@@ -145,6 +173,7 @@ struct PairGenArgs {
   int nttasks;
   int nx, ny, nz, Nx, Ny, Nz;     // local / global grid size
   int nbx, nby, nbz;              // number of blocks per axis
+  unsigned nblocks;
   double hx, hy, hz, drmin;
   unsigned int *bucket_count;     // pass 0
   const unsigned int *bucket_start;  // pass 1
@@ -206,15 +235,16 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
               const double dx = rel_dmin(max(ax, tx * B[0]) - cx, min(bx, tx * B[0] + B[0] - 1) - cx) * h[0];
               if (dx * dx + dy * dy + dz * dz > R2)
                 continue;
-              const unsigned bucket = ((unsigned)((tz * nblk[1] + ty) * nblk[0] + tx)) * kLpBuckets + X.lp0;
+              const unsigned blk = (unsigned)((tz * nblk[1] + ty) * nblk[0] + tx);
+              const unsigned bucket = ((unsigned)lp_class(X.lp0) * A.nblocks + blk) * kLpBuckets + X.lp0;
               if (PASS == 0) {
                 atomicAdd(&A.bucket_count[bucket], 1u);
               } else {
                 const unsigned pos = A.bucket_start[bucket] + atomicAdd(&A.bucket_cursor[bucket], 1u);
                 TPair P;
-                P.ttask = q;
+                P.key = (unsigned)q | ((unsigned)X.n << 21) | ((unsigned)X.lp0 << 27);
                 P.o[0] = (signed char)ox, P.o[1] = (signed char)oy, P.o[2] = (signed char)oz;
-                P.lp0 = (unsigned char)X.lp0;
+                P.pad = 0;
                 A.pairs[pos] = P;
               }
             }
@@ -225,9 +255,12 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
   }
 }
 
-// exp tables: etab[(q*3+d)*P + (g + P/2 - 1)] = exp(-zetp (g*h_d - roff_d)^2)
+// exp tables, one row of P doubles per (task, axis):
+//   row[0] = roffset,  row[1 + t] = exp(-zetp (g*h - roff)^2) with g = t - max_nb - 1
+// for g inside the cube [-nb, nb+1] and 0 outside (both ends are zero guards).
 __global__ void etab_kernel(const TTask *ttasks, const TaskDev *tasks, const int nttasks, const int P,
-                            const double hx, const double hy, const double hz, double *etab) {
+                            const int max_nb, const double hx, const double hy, const double hz,
+                            double *etab) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)nttasks * 3 * P;
   if (idx >= total)
@@ -235,12 +268,16 @@ __global__ void etab_kernel(const TTask *ttasks, const TaskDev *tasks, const int
   const int e = (int)(idx % P), d = (int)((idx / P) % 3);
   const int q = (int)(idx / ((size_t)3 * P));
   const TTask &X = ttasks[q];
-  const int g = e - (P / 2 - 1);
   double v = 0.0;
-  if (g >= -X.nb[d] && g <= X.nb[d] + 1) {
-    const double h = (d == 0) ? hx : ((d == 1) ? hy : hz);
-    const double x = g * h - X.roff[d];
-    v = exp(-tasks[X.task].zetp * x * x);
+  if (e == 0) {
+    v = X.roff[d];
+  } else {
+    const int g = e - 1 - (max_nb + 1);
+    if (g >= -X.nb[d] && g <= X.nb[d] + 1) {
+      const double h = (d == 0) ? hx : ((d == 1) ? hy : hz);
+      const double x = g * h - X.roff[d];
+      v = exp(-tasks[X.task].zetp * x * x);
+    }
   }
   etab[idx] = v;
 }
@@ -297,9 +334,23 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   tl.ntasks_tiled = (int)tt.size();
   tl.max_lp0 = max_lp0;
   tl.max_n = max_n;
+  tl.max_nb = max_nb;
   if (tt.empty())
     return;
-  B200_ASSERT(nblocks * kLpBuckets < (size_t)1 << 31, "too many grid blocks");
+  // class-sorted: a task's coefficient slot is then pure arithmetic on its index
+  std::stable_sort(tt.begin(), tt.end(),
+                   [](const TTask &a, const TTask &b) { return lp_class(a.lp0) < lp_class(b.lp0); });
+  tl.h_tt_task.resize(tt.size());
+  for (int c = 0; c <= kNumClasses; c++)
+    tl.class_tt_first[c] = 0;
+  for (size_t q = 0; q < tt.size(); q++) {
+    tl.h_tt_task[q] = tt[q].task;
+    tl.class_tt_first[lp_class(tt[q].lp0) + 1]++;
+  }
+  for (int c = 0; c < kNumClasses; c++)
+    tl.class_tt_first[c + 1] += tl.class_tt_first[c];
+  B200_ASSERT(nblocks * kLpBuckets * kNumClasses < (size_t)1 << 31, "too many grid blocks");
+  B200_ASSERT(tt.size() < ((size_t)1 << 21), "too many tasks on one level for the packed pair key");
 
   std::vector<KTabHeader> heads;
   std::vector<signed char> ktab;
@@ -308,7 +359,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
     B200_ASSERT(X.nb[0] == heads[X.n].nbx && X.nb[1] == heads[X.n].nby && X.nb[2] == heads[X.n].nbz,
                 "cube bounds disagree with the sphere table");
   tl.ktab_bytes = (int)ktab.size();
-  tl.P = 2 * (max_nb + 1);
+  tl.P = 2 * max_nb + 5;  // roff + e(-max_nb-1 .. max_nb+2)
 
   auto up = [&](auto **dst, const auto &vec) {
     using T = typename std::remove_reference<decltype(vec)>::type::value_type;
@@ -323,13 +374,14 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   // exp tables
   const size_t etab_len = (size_t)tt.size() * 3 * tl.P;
   B200_CHECK(cudaMalloc((void **)&tl.d_etab, etab_len * sizeof(double)));
+  B200_ASSERT(etab_len < ((size_t)1 << 31), "exp tables exceed 2^31 entries on one level");
   etab_kernel<<<(unsigned)((etab_len + 255) / 256), 256, 0, s>>>(tl.d_ttasks, d_tasks, (int)tt.size(), tl.P,
-                                                                h[0], h[1], h[2], tl.d_etab);
+                                                                max_nb, h[0], h[1], h[2], tl.d_etab);
   B200_CHECK(cudaGetLastError());
   count_launch();
 
   // pairs: count, scan, fill
-  const size_t nbuckets = nblocks * kLpBuckets;
+  const size_t nbuckets = nblocks * kLpBuckets * kNumClasses;
   unsigned int *d_count = nullptr, *d_start = nullptr;
   B200_CHECK(cudaMalloc((void **)&d_count, (nbuckets + 1) * sizeof(unsigned int)));
   B200_CHECK(cudaMalloc((void **)&d_start, (nbuckets + 1) * sizeof(unsigned int)));
@@ -338,7 +390,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   PA.ttasks = tl.d_ttasks, PA.nttasks = (int)tt.size();
   PA.nx = L.npts_local[0], PA.ny = L.npts_local[1], PA.nz = L.npts_local[2];
   PA.Nx = L.npts_global[0], PA.Ny = L.npts_global[1], PA.Nz = L.npts_global[2];
-  PA.nbx = nbx, PA.nby = nby, PA.nbz = nbz;
+  PA.nbx = nbx, PA.nby = nby, PA.nbz = nbz, PA.nblocks = (unsigned)nblocks;
   PA.hx = h[0], PA.hy = h[1], PA.hz = h[2], PA.drmin = drmin;
   PA.bucket_count = d_count, PA.bucket_start = d_start, PA.bucket_cursor = nullptr, PA.pairs = nullptr;
   const int pg_blocks = ((int)tt.size() + 127) / 128;
@@ -362,27 +414,42 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   B200_CHECK(cudaGetLastError());
   count_launch(4);
 
-  // work items: a block's pairs (all lp buckets, contiguous) cut into chunks
+  // work items per lp class: a block's pairs of that class (contiguous) cut into chunks
   std::vector<TWork> work;
-  const size_t target_items = (size_t)148 * 2 * kTiledWarps * 6;
+  const size_t target_items = (size_t)148 * 64;
   const int chunk = (int)std::min<size_t>(kItemPairs, std::max<size_t>(128, npairs / target_items + 1));
-  for (size_t b = 0; b < nblocks; b++) {
-    const unsigned f = start[b * kLpBuckets], e = start[(b + 1) * kLpBuckets];
-    if (e == f)
-      continue;
-    const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((size_t)nbx * nby));
-    const int cnt = (int)(e - f), nchunks = (cnt + chunk - 1) / chunk, per = (cnt + nchunks - 1) / nchunks;
-    for (int c = 0; c < nchunks; c++) {
-      TWork W;
-      W.x0 = bx * kBX, W.y0 = by * kBY, W.z0 = bz * kBZ;
-      W.first = (int)f + c * per;
-      W.last = (int)f + std::min((c + 1) * per, cnt);
-      work.push_back(W);
+  for (int cls = 0; cls < kNumClasses; cls++) {
+    tl.class_work_first[cls] = (int)work.size();
+    const size_t w0 = work.size();
+    for (size_t b = 0; b < nblocks; b++) {
+      const size_t bb = (size_t)cls * nblocks + b;
+      const unsigned f = start[bb * kLpBuckets], e = start[(bb + 1) * kLpBuckets];
+      if (e == f)
+        continue;
+      const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((size_t)nbx * nby));
+      const int cnt = (int)(e - f), nchunks = (cnt + chunk - 1) / chunk, per = (cnt + nchunks - 1) / nchunks;
+      for (int c = 0; c < nchunks; c++) {
+        TWork W;
+        W.x0 = bx * kBX, W.y0 = by * kBY, W.z0 = bz * kBZ;
+        W.first = (int)f + c * per;
+        W.last = (int)f + std::min((c + 1) * per, cnt);
+        work.push_back(W);
+      }
     }
+    // longest first; the warps of a CTA then get items of similar length
+    std::stable_sort(work.begin() + w0, work.end(),
+                     [](const TWork &a, const TWork &b) { return (a.last - a.first) > (b.last - b.first); });
   }
-  // longest first; the 8 warps of a CTA then get items of similar length
-  std::stable_sort(work.begin(), work.end(),
-                   [](const TWork &a, const TWork &b) { return (a.last - a.first) > (b.last - b.first); });
+  tl.class_work_first[kNumClasses] = (int)work.size();
+  // TaskDev ids per class (for calls whose l growth pushes a class out of the tiled range)
+  for (int cls = 0; cls < kNumClasses; cls++) {
+    std::vector<int> ids;
+    for (const TTask &X : tt)
+      if (lp_class(X.lp0) == cls)
+        ids.push_back(X.task);
+    tl.class_ntasks[cls] = (int)ids.size();
+    up(&tl.d_class_task_ids[cls], ids);
+  }
   tl.nwork = (int)work.size();
   up(&tl.d_work, work);
   B200_CHECK(cudaStreamSynchronize(s));
@@ -390,54 +457,30 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
 }
 
 inline bool tiled_supports(const TiledLevel &tl, const int max_lp) {
-  return tl.ntasks_tiled > 0 && max_lp <= kTiledMaxLp;
+  (void)max_lp;
+  return tl.ntasks_tiled > 0;
 }
 
 // ---------------------------------------------------------------------------
 // Device: the hot kernels
 // ---------------------------------------------------------------------------
 struct TiledArgs {
-  const TTask *ttasks;
   const TPair *pairs;
-  const TWork *work;
+  const TWork *work;         // work items of ONE lp class
   int nwork;
   const KTabHeader *khead;
   const signed char *ktab;
   int ktab_bytes, max_n;
-  const double *etab;
-  int P;
-  const int *tcoef;          // coefficient offset per tiled task (for this call's dl)
+  const double *etab;        // rows of P doubles per (task, axis)
+  int P, max_nb;
+  int tt_first;              // first ttask of this class
+  int coef_base, coef_stride;  // slot of ttask q: coef_base + (q - tt_first) * coef_stride
   double *coef;
   double *grid;
   int nx, ny, nz;            // npts_local
   double hx, hy, hz;
   int dl;                    // lp growth of this call
-  int lps;                   // table pitch (doubles) = max lp of the launch + 1
-  int ncmax;                 // ncoset(lps-1)
 };
-
-template <int LP> struct NCo {
-  static constexpr int value = (LP + 1) * (LP + 2) * (LP + 3) / 6;
-};
-
-// D[lz] = sum_{lx+ly <= LP-lz} C[coset(lx,ly,lz)] X[lx] Y[ly]
-template <int LP>
-__device__ __forceinline__ void column_coefs(const double *__restrict__ C, const double (&X)[LP + 1],
-                                             const double (&Y)[LP + 1], double (&D)[LP + 1]) {
-#pragma unroll
-  for (int lz = 0; lz <= LP; lz++)
-    D[lz] = 0.0;
-#pragma unroll
-  for (int ly = 0; ly <= LP; ly++) {
-#pragma unroll
-    for (int lx = 0; lx <= LP - ly; lx++) {
-      const double xy = X[lx] * Y[ly];
-#pragma unroll
-      for (int lz = 0; lz <= LP - lx - ly; lz++)
-        D[lz] = fma(C[coset(lx, ly, lz)], xy, D[lz]);
-    }
-  }
-}
 
 // Transposing warp reduction: on return lane L holds in v[0] the warp-wide sum
 // of element `idx` (returned); lanes whose idx >= N hold zeros.
@@ -511,106 +554,138 @@ template <int LP> struct IntegrateReduce {
       slice<LZ + 1>(X, Y0, Y1, S0, S1, gcoef, lane);
     }
   }
-  static __device__ __forceinline__ void run(const double (&X)[LP + 1], const double (&Y0)[LP + 1],
-                                             const double (&Y1)[LP + 1], const double (&S0)[LP + 1],
-                                             const double (&S1)[LP + 1], double *__restrict__ gcoef,
-                                             const int lane) {
-    slice<0>(X, Y0, Y1, S0, S1, gcoef, lane);
-  }
 };
 
-// One (pair, warp) step.  `wtab` is this warp's table scratch
-// [32 entries][lps]: entries 0..7 x, 8..15 y, 16..31 z.
-template <bool COLLOCATE, int LP>
-__device__ __forceinline__ void process_pair(const int lps, const double *__restrict__ wtab,
-                                             const double *__restrict__ wC, double *__restrict__ gcoef,
-                                             const int lo0, const int len0, const int lo1, const int len1,
-                                             const bool on0, const bool on1, const int wlo, const int whi,
-                                             const int li, const int lj, const int lane, double (&acc0)[kBZ],
-                                             double (&acc1)[kBZ]) {
+// The 16 planes of a block, entered at the first plane any lane needs and left
+// after the last one (both warp-uniform): no per-plane range checks.
+#define B200_PLANES(BODY)                                                      \
+  switch (wlo) {                                                               \
+  case 0: BODY(0) if (whi == 0) break;                                         \
+  case 1: BODY(1) if (whi == 1) break;                                         \
+  case 2: BODY(2) if (whi == 2) break;                                         \
+  case 3: BODY(3) if (whi == 3) break;                                         \
+  case 4: BODY(4) if (whi == 4) break;                                         \
+  case 5: BODY(5) if (whi == 5) break;                                         \
+  case 6: BODY(6) if (whi == 6) break;                                         \
+  case 7: BODY(7) if (whi == 7) break;                                         \
+  case 8: BODY(8) if (whi == 8) break;                                         \
+  case 9: BODY(9) if (whi == 9) break;                                         \
+  case 10: BODY(10) if (whi == 10) break;                                      \
+  case 11: BODY(11) if (whi == 11) break;                                      \
+  case 12: BODY(12) if (whi == 12) break;                                      \
+  case 13: BODY(13) if (whi == 13) break;                                      \
+  case 14: BODY(14) if (whi == 14) break;                                      \
+  default: BODY(15)                                                            \
+  }
+
+// One (pair, warp) step.  `ws` is this warp's scratch: [32 entries][LP+1]
+// table rows (0..7 x, 8..15 y, 16..31 z) followed by ncoset(LP) coefficients.
+template <bool COLLOCATE, int LP, int NCL>
+__device__ __forceinline__ void process_pair(double *__restrict__ ws, double *__restrict__ gcoef,
+                                             const double e, const double x, const double (&creg)[NCL],
+                                             const unsigned mask0, const unsigned mask1, const int wlo,
+                                             const int whi, const int li, const int lj, const int lane,
+                                             double (&acc0)[kBZ], double (&acc1)[kBZ]) {
+  constexpr int PITCH = LP + 1;
+  constexpr int NC = (LP + 1) * (LP + 2) * (LP + 3) / 6;
+  // scratch: my table entry times the powers of (x - xp); the coefficients
+  __syncwarp();
+  {
+    double v = e;
+    double *row = ws + lane * PITCH;
+#pragma unroll
+    for (int l = 0; l <= LP; l++) {
+      row[l] = v;
+      v *= x;
+    }
+    if (COLLOCATE) {
+#pragma unroll
+      for (int k = 0; k < NCL; k++)
+        if (lane + 32 * k < NC)
+          ws[32 * PITCH + lane + 32 * k] = creg[k];
+    }
+  }
+  __syncwarp();
+
+  const double *__restrict__ tZ = ws + 16 * PITCH;
+  const double *__restrict__ C = ws + 32 * PITCH;
   double X[LP + 1], Y0[LP + 1], Y1[LP + 1];
 #pragma unroll
   for (int l = 0; l <= LP; l++) {
-    X[l] = wtab[li * lps + l];
-    Y0[l] = wtab[(8 + lj) * lps + l];
-    Y1[l] = wtab[(12 + lj) * lps + l];
+    X[l] = ws[li * PITCH + l];
+    Y0[l] = ws[(8 + lj) * PITCH + l];
+    Y1[l] = ws[(12 + lj) * PITCH + l];
   }
-  const double *__restrict__ tZ = wtab + 16 * lps;
 
   if (COLLOCATE) {
+    // E[ly][lz] = sum_lx C[lx,ly,lz] X[lx]  (shared by both columns: same x)
+    // D_c[lz]   = sum_ly E[ly][lz] Y_c[ly]
     double D0[LP + 1], D1[LP + 1];
-    column_coefs<LP>(wC, X, Y0, D0);
-    column_coefs<LP>(wC, X, Y1, D1);
-#define B200_PLANE(p)                                                          \
+#pragma unroll
+    for (int lz = 0; lz <= LP; lz++)
+      D0[lz] = 0.0, D1[lz] = 0.0;
+#pragma unroll
+    for (int ly = 0; ly <= LP; ly++) {
+#pragma unroll
+      for (int lz = 0; lz <= LP - ly; lz++) {
+        double ev = C[coset(0, ly, lz)] * X[0];
+#pragma unroll
+        for (int lx = 1; lx <= LP - ly - lz; lx++)
+          ev = fma(C[coset(lx, ly, lz)], X[lx], ev);
+        D0[lz] = fma(ev, Y0[ly], D0[lz]);
+        D1[lz] = fma(ev, Y1[ly], D1[lz]);
+      }
+    }
+#define B200_BODY(p)                                                           \
   {                                                                            \
     double z[LP + 1];                                                          \
-    _Pragma("unroll") for (int l = 0; l <= LP; l++) z[l] = tZ[(p)*lps + l];    \
-    if ((unsigned)((p)-lo0) <= (unsigned)len0) {                               \
-      double v = acc0[p];                                                      \
-      _Pragma("unroll") for (int l = 0; l <= LP; l++) v = fma(D0[l], z[l], v); \
-      acc0[p] = v;                                                             \
+    _Pragma("unroll") for (int l = 0; l <= LP; l++) z[l] = tZ[(p)*PITCH + l];  \
+    double v0 = acc0[p], v1 = acc1[p];                                         \
+    _Pragma("unroll") for (int l = 0; l <= LP; l++) {                          \
+      v0 = fma(D0[l], z[l], v0);                                               \
+      v1 = fma(D1[l], z[l], v1);                                               \
     }                                                                          \
-    if ((unsigned)((p)-lo1) <= (unsigned)len1) {                               \
-      double v = acc1[p];                                                      \
-      _Pragma("unroll") for (int l = 0; l <= LP; l++) v = fma(D1[l], z[l], v); \
-      acc1[p] = v;                                                             \
-    }                                                                          \
+    acc0[p] = (mask0 & (1u << (p))) ? v0 : acc0[p];                            \
+    acc1[p] = (mask1 & (1u << (p))) ? v1 : acc1[p];                            \
   }
-#pragma unroll
-    for (int p = 0; p < kBZ; p++) {
-      if (p >= wlo && p <= whi)  // warp-uniform
-        B200_PLANE(p)
-    }
-#undef B200_PLANE
+    B200_PLANES(B200_BODY)
+#undef B200_BODY
   } else {
     double S0[LP + 1], S1[LP + 1];
 #pragma unroll
     for (int l = 0; l <= LP; l++)
       S0[l] = 0.0, S1[l] = 0.0;
-#pragma unroll
-    for (int p = 0; p < kBZ; p++) {
-      if (p >= wlo && p <= whi) {
-        double z[LP + 1];
-#pragma unroll
-        for (int l = 0; l <= LP; l++)
-          z[l] = tZ[p * lps + l];
-        if ((unsigned)(p - lo0) <= (unsigned)len0) {
-#pragma unroll
-          for (int l = 0; l <= LP; l++)
-            S0[l] = fma(acc0[p], z[l], S0[l]);
-        }
-        if ((unsigned)(p - lo1) <= (unsigned)len1) {
-#pragma unroll
-          for (int l = 0; l <= LP; l++)
-            S1[l] = fma(acc1[p], z[l], S1[l]);
-        }
-      }
-    }
-    // table entries outside the cube are zero, inactive columns have S = 0:
+#define B200_BODY(p)                                                           \
+  {                                                                            \
+    double z[LP + 1];                                                          \
+    _Pragma("unroll") for (int l = 0; l <= LP; l++) z[l] = tZ[(p)*PITCH + l];  \
+    const double a0 = (mask0 & (1u << (p))) ? acc0[p] : 0.0;                   \
+    const double a1 = (mask1 & (1u << (p))) ? acc1[p] : 0.0;                   \
+    _Pragma("unroll") for (int l = 0; l <= LP; l++) {                          \
+      S0[l] = fma(a0, z[l], S0[l]);                                            \
+      S1[l] = fma(a1, z[l], S1[l]);                                            \
+    }                                                                          \
+  }
+    B200_PLANES(B200_BODY)
+#undef B200_BODY
+    // table entries outside the cube are zero and inactive columns have S = 0:
     // nothing spurious enters the warp-wide sums
-#pragma unroll
-    for (int l = 0; l <= LP; l++) {
-      if (!on0)
-        Y0[l] = 0.0;
-      if (!on1)
-        Y1[l] = 0.0;
-    }
-    IntegrateReduce<LP>::run(X, Y0, Y1, S0, S1, gcoef, lane);
+    IntegrateReduce<LP>::template slice<0>(X, Y0, Y1, S0, S1, gcoef, lane);
   }
 }
 
-template <bool COLLOCATE>
-__global__ void __launch_bounds__(kTiledThreads, 2) tiled_kernel(const TiledArgs A) {
+template <bool COLLOCATE, int LPLO, int LPHI>
+__global__ void __launch_bounds__(kTiledThreads) tiled_kernel(const TiledArgs A) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lps = A.lps, ncmax = A.ncmax;
-  // shared memory: per-warp table scratch + coefficients, then the K tables
-  double *wtab = smem + (size_t)warp * (32 * lps + ncmax);
-  double *wC = wtab + 32 * lps;
-  KTabHeader *s_khead = (KTabHeader *)(smem + (size_t)kTiledWarps * (32 * lps + ncmax));
+  constexpr int NCHI = (LPHI + 1) * (LPHI + 2) * (LPHI + 3) / 6;
+  constexpr int NCL = (NCHI + 31) / 32;  // coefficient registers per lane
+  constexpr int kScratch = 32 * (LPHI + 1) + NCHI;
+  double *ws = smem + (size_t)warp * kScratch;
+  int4 *s_khead = (int4 *)(smem + (size_t)kTiledWarps * kScratch);
   signed char *s_ktab = (signed char *)(s_khead + (A.max_n + 1));
   for (int q = tid; q <= A.max_n; q += kTiledThreads)
-    s_khead[q] = A.khead[q];
+    s_khead[q] = ((const int4 *)A.khead)[q];
   for (int q = tid; q < A.ktab_bytes; q += kTiledThreads)
     s_ktab[q] = A.ktab[q];
   __syncthreads();  // the only CTA-wide barrier
@@ -625,6 +700,7 @@ __global__ void __launch_bounds__(kTiledThreads, 2) tiled_kernel(const TiledArgs
   double *g0 = A.grid + (size_t)W.z0 * sz + (size_t)(W.y0 + lj) * sy + W.x0 + li;
   double *g1 = g0 + 4 * sy;
   const bool col0 = (li < vx && lj < vy), col1 = (li < vx && lj + 4 < vy);
+  const unsigned vzmask = (vz >= 16) ? 0xffffu : ((1u << vz) - 1u);
 
   double acc0[kBZ], acc1[kBZ];
 #pragma unroll
@@ -642,93 +718,77 @@ __global__ void __launch_bounds__(kTiledThreads, 2) tiled_kernel(const TiledArgs
   const int my_axis = (lane < 8) ? 0 : ((lane < 16) ? 1 : 2);
   const int my_t = (lane < 8) ? lane : ((lane < 16) ? lane - 8 : lane - 16);
   const double my_h = (my_axis == 0) ? A.hx : ((my_axis == 1) ? A.hy : A.hz);
-  const int Phalf = A.P / 2 - 1;
+  const int oshift = 24 - 8 * my_axis;           // sign-extending extraction of o[my_axis]
+  const int row3 = 3 * A.P;
+  const double *__restrict__ etab_axis = A.etab + my_axis * A.P;
+  const int gbias = my_t + A.max_nb + 1;         // etab entry index = gbias - o
+  const int ge_max = A.P - 2;
+  const double *__restrict__ coef_lane = A.coef + A.coef_base + lane;
 
-  // ---- software pipeline: fetch(pair) -> process(pair) ----------------------
-  TPair Pn = A.pairs[W.first];
-  double e_n, roff_n, c_n = 0.0;
-  int n_n, coff_n;
-  {
-    const TTask &X = A.ttasks[Pn.ttask];
-    n_n = X.n;
-    roff_n = X.roff[my_axis];
-    coff_n = A.tcoef[Pn.ttask];
-    const int g = my_t - Pn.o[my_axis];
-    const int ge = min(max(g + Phalf, 0), A.P - 1);
-    e_n = A.etab[((size_t)Pn.ttask * 3 + my_axis) * A.P + ge];
-    if (g + Phalf != ge)
-      e_n = 0.0;
-    if (COLLOCATE && lane < ncoset(Pn.lp0 + A.dl))
-      c_n = A.coef[coff_n + lane];
+  // ---- software pipeline: fetch(pair ip+1) while processing pair ip -----------
+  const uint2 *__restrict__ pairs2 = (const uint2 *)A.pairs;
+  uint2 Pn = pairs2[W.first];
+  double e_n, roff_n, c_n[NCL];
+  int o_n;
+#define B200_FETCH()                                                           \
+  {                                                                            \
+    const int q_ = (int)(Pn.x & 0x1fffffu);                                    \
+    const double *row_ = etab_axis + q_ * row3;                                \
+    o_n = ((int)(Pn.y << oshift)) >> 24;                                       \
+    const int ge_ = min(max(gbias - o_n, 0), ge_max);                          \
+    roff_n = row_[0];                                                          \
+    e_n = row_[1 + ge_];                                                       \
+    if (COLLOCATE) {                                                           \
+      const double *c_ = coef_lane + (q_ - A.tt_first) * A.coef_stride;        \
+      _Pragma("unroll") for (int k = 0; k < NCL; k++)                          \
+        c_n[k] = (lane + 32 * k < NCHI) ? c_[32 * k] : 0.0;                    \
+    }                                                                          \
   }
+  B200_FETCH()
 
   for (int ip = W.first; ip < W.last; ip++) {
-    const TPair P = Pn;
+    const uint2 P = Pn;
     const double e = e_n, roff = roff_n;
-    double c0 = c_n;
-    const int n = n_n, coff = coff_n;
-    const int lp = P.lp0 + A.dl;
-    if (ip + 1 < W.last) {  // prefetch the next pair
-      Pn = A.pairs[ip + 1];
-      const TTask &X = A.ttasks[Pn.ttask];
-      n_n = X.n;
-      roff_n = X.roff[my_axis];
-      coff_n = A.tcoef[Pn.ttask];
-      const int g = my_t - Pn.o[my_axis];
-      const int ge = min(max(g + Phalf, 0), A.P - 1);
-      e_n = A.etab[((size_t)Pn.ttask * 3 + my_axis) * A.P + ge];
-      if (g + Phalf != ge)
-        e_n = 0.0;
-      if (COLLOCATE && lane < ncoset(Pn.lp0 + A.dl))
-        c_n = A.coef[coff_n + lane];
+    double creg[NCL];
+#pragma unroll
+    for (int k = 0; k < NCL; k++)
+      creg[k] = COLLOCATE ? c_n[k] : 0.0;
+    const int o_mine = o_n;
+    if (ip + 1 < W.last) {
+      Pn = pairs2[ip + 1];
+      B200_FETCH()
     }
+    const int lp = (int)(P.x >> 27) + A.dl;
+    const int ox = ((int)(P.y << 24)) >> 24, oy = ((int)(P.y << 16)) >> 24, oz = ((int)(P.y << 8)) >> 24;
 
-    // admissible planes of my two columns
-    const KTabHeader H = s_khead[n];
-    const int mi = pair_dist(li - P.o[0]);
-    const int px = H.nbx + 1;
-    int lo[2], len[2], hi[2];
+    // admissible planes of my two columns, as 16-bit masks
+    const int4 H = s_khead[(P.x >> 21) & 63u];  // offset, nbx, nby, nbz
+    const int wx = 2 * H.y + 2;
+    const unsigned ti = (unsigned)(li - ox + H.y);
+    unsigned mask[2];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-      const int j = lj + 4 * c;
-      const int mj = pair_dist(j - P.o[1]);
+      const unsigned tj = (unsigned)(lj + 4 * c - oy + H.z);
       int K = -1;
-      if (mi <= H.nbx && mj <= H.nby && (c == 0 ? col0 : col1))
-        K = s_ktab[H.offset + mj * px + mi];
-      const int plo = max(P.o[2] - K, 0), phi = min(P.o[2] + K + 1, vz - 1);
-      const bool on = (K >= 0 && plo <= phi);
-      // inactive column: (unsigned)(p - lo) <= (unsigned)len is never true
-      lo[c] = on ? plo : (1 << 20);
-      len[c] = on ? phi - plo : 0;
-      hi[c] = on ? phi : -1;
+      if (ti < (unsigned)wx && tj < (unsigned)(2 * H.z + 2) && (c == 0 ? col0 : col1))
+        K = s_ktab[H.x + (int)tj * wx + (int)ti];
+      // planes p with pair_dist(p - oz) <= K  <=>  oz - K <= p <= oz + K + 1
+      const int plo = max(oz - K, 0), phi = min(oz + K + 1, 15);
+      mask[c] = (K >= 0 && plo <= phi) ? (((2u << (phi - plo)) - 1u) << plo) & vzmask : 0u;
     }
-    const int wlo = __reduce_min_sync(0xffffffffu, min(lo[0], lo[1]));
-    const int whi = __reduce_max_sync(0xffffffffu, max(hi[0], hi[1]));
-    if (wlo > whi)
+    const unsigned wmask = __reduce_or_sync(0xffffffffu, mask[0] | mask[1]);
+    if (wmask == 0u)
       continue;  // warp-uniform: the sphere misses this block after all
+    const int wlo = __ffs(wmask) - 1, whi = 31 - __clz(wmask);
+    const double x = (my_t - o_mine) * my_h - roff;
+    double *gcoef = A.coef + A.coef_base + ((int)(P.x & 0x1fffffu) - A.tt_first) * A.coef_stride;
 
-    // table scratch: my entry times the powers of (x - xp)
-    __syncwarp();
-    {
-      const double x = (my_t - P.o[my_axis]) * my_h - roff;
-      double v = e;
-      double *row = wtab + lane * lps;
-      for (int l = 0; l <= lp; l++, v *= x)
-        row[l] = v;
-      if (COLLOCATE && lane < ncmax)
-        wC[lane] = c0;
-      if (COLLOCATE)
-        for (int c = lane + 32; c < ncoset(lp); c += 32)
-          wC[c] = A.coef[coff + c];
-    }
-    __syncwarp();
-
-    double *gcoef = A.coef + coff;
     switch (lp) {
 #define B200_CASE(LPV)                                                                             \
   case LPV:                                                                                        \
-    process_pair<COLLOCATE, LPV>(lps, wtab, wC, gcoef, lo[0], len[0], lo[1], len[1], hi[0] >= 0,   \
-                                 hi[1] >= 0, wlo, whi, li, lj, lane, acc0, acc1);                  \
+    if constexpr (LPV >= LPLO && LPV <= LPHI)                                                      \
+      process_pair<COLLOCATE, LPV, NCL>(ws, gcoef, e, x, creg, mask[0], mask[1], wlo, whi, li, lj, \
+                                        lane, acc0, acc1);                                         \
     break;
       B200_CASE(0)
       B200_CASE(1)
@@ -742,6 +802,7 @@ __global__ void __launch_bounds__(kTiledThreads, 2) tiled_kernel(const TiledArgs
       break;
     }
   }
+#undef B200_FETCH
 
   if (COLLOCATE) {
 #pragma unroll
@@ -756,47 +817,66 @@ __global__ void __launch_bounds__(kTiledThreads, 2) tiled_kernel(const TiledArgs
   }
 }
 
-inline size_t tiled_smem_bytes(const int lps, const int max_n, const int ktab_bytes) {
-  const size_t nd = (size_t)kTiledWarps * (32 * lps + ncoset(lps - 1));
+inline size_t tiled_smem_bytes(const int lphi, const int max_n, const int ktab_bytes) {
+  const size_t nd = (size_t)kTiledWarps * (32 * (lphi + 1) + ncoset(lphi));
   return nd * sizeof(double) + (max_n + 1) * sizeof(KTabHeader) + ktab_bytes + 16;
 }
 
-inline void launch_tiled(TiledLevel &tl, const GridLaunch &L, const bool collocate) {
-  if (tl.nwork == 0)
-    return;
+template <bool COLLOCATE, int LPLO, int LPHI>
+inline void launch_tiled_class(const TiledArgs &A, const TiledLevel &tl, cudaStream_t s) {
+  const size_t bytes = tiled_smem_bytes(LPHI, tl.max_n, tl.ktab_bytes);
+  B200_ASSERT(bytes <= 200 * 1024, "tiled kernel: shared memory budget exceeded");
+  B200_CHECK(cudaFuncSetAttribute(tiled_kernel<COLLOCATE, LPLO, LPHI>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  const int grid = (A.nwork + kTiledWarps - 1) / kTiledWarps;
+  tiled_kernel<COLLOCATE, LPLO, LPHI><<<grid, kTiledThreads, bytes, s>>>(A);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+// Launches the tiled kernels of every lp class that stays within the tiled
+// range for this call's l growth; returns a bit mask of the classes that must
+// be handled by the generic kernel instead.
+template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const GridLaunch &L) {
+  if (tl.ntasks_tiled == 0)
+    return 0u;
   B200_ASSERT(L.dl >= 0 && L.dl < 8, "unexpected l growth");
-  if (tl.d_tcoef[L.dl] == nullptr) {  // coefficient offsets per tiled task for this dl
-    B200_CHECK(cudaMalloc((void **)&tl.d_tcoef[L.dl], tl.ntasks_tiled * sizeof(int)));
-    tcoef_kernel<<<(tl.ntasks_tiled + 255) / 256, 256, 0, L.stream>>>(tl.d_ttasks, tl.ntasks_tiled,
-                                                                      L.coef_offsets, tl.d_tcoef[L.dl]);
-    B200_CHECK(cudaGetLastError());
-    count_launch();
-  }
   TiledArgs A;
-  A.ttasks = tl.d_ttasks, A.pairs = tl.d_pairs, A.work = tl.d_work, A.nwork = tl.nwork;
+  A.pairs = tl.d_pairs;
   A.khead = tl.d_khead, A.ktab = tl.d_ktab, A.ktab_bytes = tl.ktab_bytes, A.max_n = tl.max_n;
-  A.etab = tl.d_etab, A.P = tl.P, A.tcoef = tl.d_tcoef[L.dl];
+  A.etab = tl.d_etab, A.P = tl.P, A.max_nb = tl.max_nb;
   A.coef = L.coef, A.grid = L.grid;
   A.nx = L.level.npts_local[0], A.ny = L.level.npts_local[1], A.nz = L.level.npts_local[2];
   A.hx = L.level.dh[0], A.hy = L.level.dh[4], A.hz = L.level.dh[8];
   A.dl = L.dl;
-  A.lps = tl.max_lp0 + L.dl + 1;
-  A.ncmax = ncoset(A.lps - 1);
-  const size_t bytes = tiled_smem_bytes(A.lps, tl.max_n, tl.ktab_bytes);
-  B200_ASSERT(bytes <= 100 * 1024, "tiled kernel: shared memory budget exceeded");
-  const int grid = (tl.nwork + kTiledWarps - 1) / kTiledWarps;
-  if (collocate) {
-    B200_CHECK(cudaFuncSetAttribute(tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    tiled_kernel<true><<<grid, kTiledThreads, bytes, L.stream>>>(A);
-  } else {
-    B200_CHECK(cudaFuncSetAttribute(tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    tiled_kernel<false><<<grid, kTiledThreads, bytes, L.stream>>>(A);
+  unsigned leftover = 0u;
+  for (int cls = 0; cls < kNumClasses; cls++) {
+    A.work = tl.d_work + tl.class_work_first[cls];
+    A.nwork = tl.class_work_first[cls + 1] - tl.class_work_first[cls];
+    if (A.nwork == 0)
+      continue;
+    const int lo = kClassLo[cls] + L.dl, hi = kClassHi[cls] + L.dl;
+    if (hi > kTiledMaxLp) {
+      leftover |= 1u << cls;
+      continue;
+    }
+    A.tt_first = tl.class_tt_first[cls];
+    A.coef_base = tl.coef_base[L.dl][cls];
+    A.coef_stride = ncoset(hi);
+    cudaStream_t s = L.stream;
+    if (lo == 0) launch_tiled_class<COLLOCATE, 0, 2>(A, tl, s);
+    else if (lo == 1) launch_tiled_class<COLLOCATE, 1, 3>(A, tl, s);
+    else if (lo == 2) launch_tiled_class<COLLOCATE, 2, 4>(A, tl, s);
+    else if (lo == 3 && hi == 5) launch_tiled_class<COLLOCATE, 3, 5>(A, tl, s);
+    else if (lo == 3) launch_tiled_class<COLLOCATE, 3, 4>(A, tl, s);
+    else if (lo == 4 && hi == 6) launch_tiled_class<COLLOCATE, 4, 6>(A, tl, s);
+    else if (lo == 4) launch_tiled_class<COLLOCATE, 4, 5>(A, tl, s);
+    else if (lo == 5) launch_tiled_class<COLLOCATE, 5, 6>(A, tl, s);
+    else if (lo == 6) launch_tiled_class<COLLOCATE, 6, 6>(A, tl, s);
+    else leftover |= 1u << cls;
   }
-  B200_CHECK(cudaGetLastError());
-  count_launch();
+  return leftover;
 }
-inline void launch_tiled_collocate(TiledLevel &tl, const GridLaunch &L) { launch_tiled(tl, L, true); }
-inline void launch_tiled_integrate(TiledLevel &tl, const GridLaunch &L) { launch_tiled(tl, L, false); }
 
 // ---------------------------------------------------------------------------
 // Workload statistics: walks the reference's loop bounds for every task and

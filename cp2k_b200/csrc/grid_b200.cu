@@ -258,16 +258,35 @@ static void ensure_transforms(TaskList &tl, int dl, cudaStream_t s) {
     tl.d_Tptrs.upload(tl.h_Tptrs, s);
 }
 
+// Coefficient buffer layout for one l growth `dl`.  Tasks on the tiled path
+// get fixed-size slots per (level, lp class) so that the hot kernels compute a
+// task's slot from its index without a load; all other tasks are packed behind.
 static void ensure_coef_offsets(TaskList &tl, int dl, cudaStream_t s) {
   B200_ASSERT(dl >= 0 && dl < 8, "unexpected l growth");
   if (tl.coef_ready[dl])
     return;
-  std::vector<int> off(tl.ntasks);
+  std::vector<int> off(tl.ntasks, -1);
   size_t total = 0;
-  for (int i = 0; i < tl.ntasks; i++) {
-    off[i] = (int)total;
-    total += ncoset(tl.h_tasks[i].la_max + tl.h_tasks[i].lb_max + dl);
+  for (int lev = 0; lev < tl.nlevels; lev++) {
+    TiledLevel &T = tl.linfo[lev].tiled;
+    for (int cls = 0; cls < kNumClasses; cls++) {
+      const int stride = ncoset(kClassHi[cls] + dl);
+      B200_ASSERT(total < (size_t)INT_MAX, "coefficient buffer exceeds 2^31 entries");
+      T.coef_base[dl][cls] = (int)total;
+      if (T.ntasks_tiled == 0)
+        continue;
+      for (int q = T.class_tt_first[cls]; q < T.class_tt_first[cls + 1]; q++) {
+        off[T.h_tt_task[q]] = (int)total;
+        total += stride;
+      }
+    }
   }
+  for (int i = 0; i < tl.ntasks; i++)
+    if (off[i] < 0) {
+      off[i] = (int)total;
+      total += ncoset(tl.h_tasks[i].la_max + tl.h_tasks[i].lb_max + dl);
+    }
+  total += 256;  // slack for whole-slot prefetches
   B200_ASSERT(total < (size_t)INT_MAX, "coefficient buffer exceeds 2^31 entries");
   tl.d_coef_off[dl].upload(off, s);
   tl.coef_total[dl] = total;
@@ -686,9 +705,14 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
         GL.task_ids = tl.d_iota.p + li.first, GL.ntasks = li.last - li.first;
         launch_generic(GL, true);
       } else {
-        launch_tiled_collocate(li.tiled, GL);
+        const unsigned leftover = launch_tiled<true>(li.tiled, GL);
         GL.task_ids = tl.d_generic_ids.p + tl.generic_first[l], GL.ntasks = li.n_generic;
         launch_generic(GL, true);
+        for (int cls = 0; cls < kNumClasses; cls++)
+          if (leftover & (1u << cls)) {
+            GL.task_ids = li.tiled.d_class_task_ids[cls], GL.ntasks = li.tiled.class_ntasks[cls];
+            launch_generic(GL, true);
+          }
       }
     }
     if (!resident) {
@@ -771,9 +795,14 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
       GL.task_ids = tl.d_iota.p + li.first, GL.ntasks = li.last - li.first;
       launch_generic(GL, false);
     } else {
-      launch_tiled_integrate(li.tiled, GL);
+      const unsigned leftover = launch_tiled<false>(li.tiled, GL);
       GL.task_ids = tl.d_generic_ids.p + tl.generic_first[l], GL.ntasks = li.n_generic;
       launch_generic(GL, false);
+      for (int cls = 0; cls < kNumClasses; cls++)
+        if (leftover & (1u << cls)) {
+          GL.task_ids = li.tiled.d_class_task_ids[cls], GL.ntasks = li.tiled.class_ntasks[cls];
+          launch_generic(GL, false);
+        }
     }
   }
 
