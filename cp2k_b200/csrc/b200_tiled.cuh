@@ -369,6 +369,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   };
   up(&tl.d_ttasks, tt);
   up(&tl.d_khead, heads);
+  ktab.resize((ktab.size() + 15) / 16 * 16, (signed char)-1);  // copied as 16-byte words
   up(&tl.d_ktab, ktab);
 
   // exp tables
@@ -670,12 +671,30 @@ __device__ __forceinline__ void process_pair(double *__restrict__ ws, double *__
 #undef B200_BODY
     // table entries outside the cube are zero and inactive columns have S = 0:
     // nothing spurious enters the warp-wide sums
-    IntegrateReduce<LP>::template slice<0>(X, Y0, Y1, S0, S1, gcoef, lane);
+    if constexpr (LP <= 3) {
+      // few coefficients: one transposing reduction over all of them
+      double part[NC];
+#pragma unroll
+      for (int ly = 0; ly <= LP; ly++) {
+#pragma unroll
+        for (int lz = 0; lz <= LP - ly; lz++) {
+          const double w = fma(Y0[ly], S0[lz], Y1[ly] * S1[lz]);
+#pragma unroll
+          for (int lx = 0; lx <= LP - ly - lz; lx++)
+            part[coset(lx, ly, lz)] = X[lx] * w;
+        }
+      }
+      const int idx = WarpVecReduce<NC>::run(part, lane);
+      if ((lane & (DupLanes<NC>::value - 1)) == 0 && idx < NC && part[0] != 0.0)
+        atomicAdd(&gcoef[idx], part[0]);
+    } else {
+      IntegrateReduce<LP>::template slice<0>(X, Y0, Y1, S0, S1, gcoef, lane);
+    }
   }
 }
 
 template <bool COLLOCATE, int LPLO, int LPHI>
-__global__ void __launch_bounds__(kTiledThreads) tiled_kernel(const TiledArgs A) {
+__global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kernel(const TiledArgs A) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NCHI = (LPHI + 1) * (LPHI + 2) * (LPHI + 3) / 6;
@@ -686,13 +705,12 @@ __global__ void __launch_bounds__(kTiledThreads) tiled_kernel(const TiledArgs A)
   signed char *s_ktab = (signed char *)(s_khead + (A.max_n + 1));
   for (int q = tid; q <= A.max_n; q += kTiledThreads)
     s_khead[q] = ((const int4 *)A.khead)[q];
-  for (int q = tid; q < A.ktab_bytes; q += kTiledThreads)
-    s_ktab[q] = A.ktab[q];
+  for (int q = tid; q < (A.ktab_bytes + 15) / 16; q += kTiledThreads)
+    ((int4 *)s_ktab)[q] = ((const int4 *)A.ktab)[q];
   __syncthreads();  // the only CTA-wide barrier
 
-  const int iw = blockIdx.x * kTiledWarps + warp;
-  if (iw >= A.nwork)
-    return;
+  // persistent warps: work items (sorted longest first) are dealt round-robin
+  for (int iw = blockIdx.x * kTiledWarps + warp; iw < A.nwork; iw += gridDim.x * kTiledWarps) {
   const TWork W = A.work[iw];
   const int vx = min(kBX, A.nx - W.x0), vy = min(kBY, A.ny - W.y0), vz = min(kBZ, A.nz - W.z0);
   const int li = lane & 7, lj = lane >> 3;  // my columns: (li, lj) and (li, lj + 4)
@@ -728,6 +746,7 @@ __global__ void __launch_bounds__(kTiledThreads) tiled_kernel(const TiledArgs A)
   // ---- software pipeline: fetch(pair ip+1) while processing pair ip -----------
   const uint2 *__restrict__ pairs2 = (const uint2 *)A.pairs;
   uint2 Pn = pairs2[W.first];
+  uint2 Pnn = pairs2[min(W.first + 1, W.last - 1)];
   double e_n, roff_n, c_n[NCL];
   int o_n;
 #define B200_FETCH()                                                           \
@@ -755,8 +774,9 @@ __global__ void __launch_bounds__(kTiledThreads) tiled_kernel(const TiledArgs A)
       creg[k] = COLLOCATE ? c_n[k] : 0.0;
     const int o_mine = o_n;
     if (ip + 1 < W.last) {
-      Pn = pairs2[ip + 1];
+      Pn = Pnn;  // record fetched one iteration ago: its dependent loads start now
       B200_FETCH()
+      Pnn = pairs2[min(ip + 2, W.last - 1)];
     }
     const int lp = (int)(P.x >> 27) + A.dl;
     const int ox = ((int)(P.y << 24)) >> 24, oy = ((int)(P.y << 16)) >> 24, oz = ((int)(P.y << 8)) >> 24;
@@ -802,7 +822,6 @@ __global__ void __launch_bounds__(kTiledThreads) tiled_kernel(const TiledArgs A)
       break;
     }
   }
-#undef B200_FETCH
 
   if (COLLOCATE) {
 #pragma unroll
@@ -815,11 +834,13 @@ __global__ void __launch_bounds__(kTiledThreads) tiled_kernel(const TiledArgs A)
       }
     }
   }
+  }  // work items
+#undef B200_FETCH
 }
 
 inline size_t tiled_smem_bytes(const int lphi, const int max_n, const int ktab_bytes) {
   const size_t nd = (size_t)kTiledWarps * (32 * (lphi + 1) + ncoset(lphi));
-  return nd * sizeof(double) + (max_n + 1) * sizeof(KTabHeader) + ktab_bytes + 16;
+  return nd * sizeof(double) + (max_n + 1) * sizeof(KTabHeader) + ktab_bytes + 32;
 }
 
 template <bool COLLOCATE, int LPLO, int LPHI>
@@ -828,7 +849,10 @@ inline void launch_tiled_class(const TiledArgs &A, const TiledLevel &tl, cudaStr
   B200_ASSERT(bytes <= 200 * 1024, "tiled kernel: shared memory budget exceeded");
   B200_CHECK(cudaFuncSetAttribute(tiled_kernel<COLLOCATE, LPLO, LPHI>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  const int grid = (A.nwork + kTiledWarps - 1) / kTiledWarps;
+  int per_sm = 1;
+  B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiled_kernel<COLLOCATE, LPLO, LPHI>,
+                                                          kTiledThreads, bytes));
+  const int grid = std::min((A.nwork + kTiledWarps - 1) / kTiledWarps, 148 * std::max(per_sm, 1));
   tiled_kernel<COLLOCATE, LPLO, LPHI><<<grid, kTiledThreads, bytes, s>>>(A);
   B200_CHECK(cudaGetLastError());
   count_launch();
