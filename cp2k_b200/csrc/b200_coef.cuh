@@ -25,8 +25,17 @@ __constant__ double c_binom[kMaxLSide + 1][kMaxLSide + 1];
 struct Orb {
   int l[3];
 };
-__device__ inline Orb orb_of(const int c) {
-  return Orb{{c_orb.l[c][0], c_orb.l[c][1], c_orb.l[c][2]}};
+// The orbital table is staged into shared memory by every kernel that decodes
+// coset indices with lane-varying arguments: divergent __constant__ reads are
+// serialised, shared-memory reads are not.
+constexpr int kOrbEntries = 816;  // ncoset(15)
+__device__ inline void stage_orb_table(unsigned *s_orb, const int tid, const int nthr) {
+  for (int c = tid; c < kOrbEntries; c += nthr)
+    s_orb[c] = (unsigned)c_orb.l[c][0] | ((unsigned)c_orb.l[c][1] << 8) | ((unsigned)c_orb.l[c][2] << 16);
+}
+__device__ inline Orb orb_of(const unsigned *__restrict__ s_orb, const int c) {
+  const unsigned v = s_orb[c];
+  return Orb{{(int)(v & 255u), (int)((v >> 8) & 255u), (int)(v >> 16)}};
 }
 __device__ inline int oidx(const Orb &a) { return coset(a.l[0], a.l[1], a.l[2]); }
 __device__ inline Orb oup(const int i, Orb a) {
@@ -235,6 +244,9 @@ __global__ void __launch_bounds__(128)
 pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
                    const CoefDims D) {
   extern __shared__ double smem[];
+  __shared__ unsigned s_orb[kOrbEntries];
+  stage_orb_table(s_orb, threadIdx.x, blockDim.x);
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
   double *s_work = smem + (size_t)warp * D.total();
@@ -277,7 +289,7 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
       if (func == 100) {
         s_cab[ib * n1c + ia] = p;  // identity: distinct targets
       } else {
-        const Orb a = orb_of(ia), b = orb_of(ib);
+        const Orb a = orb_of(s_orb, ia), b = orb_of(s_orb, ib);
         for (int tt = 0; tt < F.nterms; tt++) {
           OpTerm ta[4], tb[4];
           const int na_t = op_expand(F.t[tt].a, a, T.zeta, ta);
@@ -299,12 +311,12 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
     const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
     const bool to_cijk = !T.use_ortho;
     for (int c = lane; c < nc; c += 32) {
-      const Orb k = orb_of(c);
+      const Orb k = orb_of(s_orb, c);
       double acc = 0.0;
       for (int ib = cb_lo; ib < n2c; ib++) {
-        const Orb b = orb_of(ib);
+        const Orb b = orb_of(s_orb, ib);
         for (int ia = ca_lo; ia < n1c; ia++) {
-          const Orb a = orb_of(ia);
+          const Orb a = orb_of(s_orb, ia);
           if (k.l[0] <= a.l[0] + b.l[0] && k.l[1] <= a.l[1] + b.l[1] &&
               k.l[2] <= a.l[2] + b.l[2]) {
             acc += s_cab[ib * n1c + ia] *
@@ -384,48 +396,32 @@ __device__ inline double vab_elem(const PCtx &p, const bool tau, const int what,
 }
 
 struct HabDims {
-  int work, raw, cab, alpha, cxyz, h, block;  // doubles
-  __host__ __device__ int total() const { return work + raw + cab + alpha + 2 * cxyz + h + block; }
+  int work, raw, cab, alpha, cxyz, h;  // doubles per warp
+  __host__ __device__ int total() const { return work + raw + cab + alpha + 2 * cxyz + h; }
 };
 
-constexpr int kHabThreads = 128;
-
-__global__ void __launch_bounds__(kHabThreads)
-coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int dla_max,
-                   const int dla_min, const int dlb_max, const int dlb_min,
-                   const bool block_in_smem) {
+// One warp per task (tasks visited in block order for locality).  The spherical
+// block receives the task's contribution through FP64 atomics: tasks of one
+// block are few (~8 for water) and the atomics are spread over the whole block.
+__global__ void __launch_bounds__(128)
+coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const int dla_max,
+                   const int dla_min, const int dlb_max, const int dlb_min) {
   extern __shared__ double smem[];
-  double *s_work = smem;
+  __shared__ unsigned s_orb[kOrbEntries];
+  stage_orb_table(s_orb, threadIdx.x, blockDim.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  double *s_work = smem + (size_t)warp * D.total();
   double *s_raw = s_work + D.work;
   double *s_cab = s_raw + D.raw;
   double *s_alpha = s_cab + D.cab;
   double *s_cxyz = s_alpha + D.alpha;
   double *s_cijk = s_cxyz + D.cxyz;
   double *s_h = s_cijk + D.cxyz;
-  double *s_block = s_h + D.h;
-  __shared__ double s_red[kHabThreads / 32][15];
-  const int t = threadIdx.x;
-  auto sync = [] { __syncthreads(); };
-
-  const int iblock = blockIdx.x;
-  const int first = L.block_first[iblock], last = L.block_first[iblock + 1];
-  if (first >= last)
-    return;
+  auto sync = [] { __syncwarp(); };
   const bool do_f = (L.forces != nullptr), do_v = (L.virial != nullptr);
-  double facc[15];  // force a (3), force b (3), virial a+b (9)
-  for (int i = 0; i < 15; i++)
-    facc[i] = 0.0;
 
-  const TaskDev &T0 = L.tasks[L.block_task_ids[first]];
-  const int blk_size = T0.nsgfa * T0.nsgfb;
-  double *g_block = L.hab + T0.block_offset;
-  if (block_in_smem) {
-    for (int q = t; q < blk_size; q += kHabThreads)
-      s_block[q] = 0.0;
-  }
-  __syncthreads();
-
-  for (int it = first; it < last; it++) {
+  for (int it = blockIdx.x * wpc + warp; it < ntasks; it += gridDim.x * wpc) {
     const int itask = L.block_task_ids[it];
     const TaskDev &T = L.tasks[itask];
     if (T.skip)
@@ -438,30 +434,30 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int dla_max,
 
     // (1) coefficients, back to the Cartesian polynomial basis if needed
     if (T.use_ortho) {
-      for (int c = t; c < nc; c += kHabThreads)
+      for (int c = lane; c < nc; c += 32)
         s_cxyz[c] = in[c];
     } else {
-      for (int c = t; c < nc; c += kHabThreads)
+      for (int c = lane; c < nc; c += 32)
         s_cijk[c] = in[c];
-      __syncthreads();
+      __syncwarp();
       const double *Tm = L.cijk_T[T.level * (kMaxLp + 1) + lp];
-      for (int c = t; c < nc; c += kHabThreads) {
+      for (int c = lane; c < nc; c += 32) {
         double acc = 0.0;
         for (int q = 0; q < nc; q++)
           acc += __ldg(&Tm[q * nc + c]) * s_cijk[q];
         s_cxyz[c] = acc;
       }
     }
-    make_alpha(T, la_c, lb_c, s_alpha, t, kHabThreads, sync);  // syncs
+    make_alpha(T, la_c, lb_c, s_alpha, lane, 32, sync);  // syncs
 
     // (2) cab[b][a] = prefactor * sum_k cxyz[k] ax ay az
     const int n1c = ncoset(la_c), n2c = ncoset(lb_c);
     const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
-    for (int q = t; q < n1c * n2c; q += kHabThreads) {
+    for (int q = lane; q < n1c * n2c; q += 32) {
       const int ia = q % n1c, ib = q / n1c;
       double acc = 0.0;
       if (ia >= ca_lo && ib >= cb_lo) {
-        const Orb a = orb_of(ia), b = orb_of(ib);
+        const Orb a = orb_of(s_orb, ia), b = orb_of(s_orb, ib);
         for (int kz = 0; kz <= a.l[2] + b.l[2]; kz++)
           for (int ky = 0; ky <= a.l[1] + b.l[1]; ky++)
             for (int kx = 0; kx <= a.l[0] + b.l[0]; kx++)
@@ -474,9 +470,8 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int dla_max,
     }
     // (3) density sub-block for forces / virial
     if (do_f || do_v)
-      decontract_task(T, L.pab + T.block_offset, L.sphi_pool, s_work, s_raw, t,
-                      kHabThreads, sync);
-    __syncthreads();
+      decontract_task(T, L.pab + T.block_offset, L.sphi_pool, s_work, s_raw, lane, 32, sync);
+    __syncwarp();
 
     // (4) matrix elements for the original l-range
     PCtx P;
@@ -484,11 +479,15 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int dla_max,
     P.rab[0] = T.rab[0], P.rab[1] = T.rab[1], P.rab[2] = T.rab[2];
     const int na = T.ncoseta, nb = T.ncosetb;
     const int a_lo = ncoset(T.la_min - 1), b_lo = ncoset(T.lb_min - 1);
-    for (int q = t; q < na * nb; q += kHabThreads) {
+    double facc[15];  // force a (3), force b (3), virial a+b (9)
+#pragma unroll
+    for (int i = 0; i < 15; i++)
+      facc[i] = 0.0;
+    for (int q = lane; q < na * nb; q += 32) {
       const int ia = q % na, ib = q / na;
       double hval = 0.0;
       if (ia >= a_lo && ib >= b_lo) {
-        const Orb a = orb_of(ia), b = orb_of(ib);
+        const Orb a = orb_of(s_orb, ia), b = orb_of(s_orb, ib);
         hval = vab_elem(P, L.compute_tau, 0, 0, 0, a, b);
         if (do_f) {
           const double pv = s_raw[ib * na + ia];
@@ -506,66 +505,50 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int dla_max,
       }
       s_h[q] = hval;
     }
-    __syncthreads();
+    __syncwarp();
 
     // (5) contract into the spherical block: block += sphi_a h sphi_b^T
     const double *sphi_a = L.sphi_pool + T.sphi_a + T.sgfa * T.maxcoa + T.o1;
     const double *sphi_b = L.sphi_pool + T.sphi_b + T.sgfb * T.maxcob + T.o2;
-    for (int q = t; q < T.nsgf_setb * na; q += kHabThreads) {
+    for (int q = lane; q < T.nsgf_setb * na; q += 32) {
       const int sb = q / na, ico = q % na;
       double acc = 0.0;
       for (int jco = 0; jco < nb; jco++)
         acc += __ldg(&sphi_b[sb * T.maxcob + jco]) * s_h[jco * na + ico];
       s_work[q] = acc;
     }
-    __syncthreads();
-    for (int q = t; q < T.nsgf_seta * T.nsgf_setb; q += kHabThreads) {
+    __syncwarp();
+    double *g_block = L.hab + T.block_offset;
+    for (int q = lane; q < T.nsgf_seta * T.nsgf_setb; q += 32) {
       const int sa = q % T.nsgf_seta, sb = q / T.nsgf_seta;
       double acc = 0.0;
       for (int ico = 0; ico < na; ico++)
         acc += s_work[sb * na + ico] * __ldg(&sphi_a[sa * T.maxcoa + ico]);
-      const int ix = block_index(T, sa, sb);
-      if (block_in_smem)
-        s_block[ix] += acc;
-      else
-        atomicAdd(&g_block[ix], acc);
+      if (acc != 0.0)
+        atomicAdd(&g_block[block_index(T, sa, sb)], acc);
     }
-    __syncthreads();
-  }
 
-  if (block_in_smem) {
-    // atomics keep aliased block offsets (src/grid/grid_replay.c:175-176) safe
-    for (int q = t; q < blk_size; q += kHabThreads)
-      if (s_block[q] != 0.0)
-        atomicAdd(&g_block[q], s_block[q]);
-  }
-
-  if (do_f) {
-    const int nred = do_v ? 15 : 6;
-    const int lane = t & 31, warp = t >> 5;
-    for (int i = 0; i < nred; i++) {
-      double v = facc[i];
-      for (int o = 16; o > 0; o >>= 1)
-        v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0)
-        s_red[warp][i] = v;
+    // (6) forces / virial of this task (src/grid/ref/grid_ref_task_list.c:625-641)
+    if (do_f) {
+      const int nred = do_v ? 15 : 6;
+      const double scale = (T.iatom == T.jatom) ? 1.0 : 2.0;
+      for (int i = 0; i < nred; i++) {
+        double v = facc[i];
+        for (int o = 16; o > 0; o >>= 1)
+          v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0.0) {
+          if (i < 3)
+            atomicAdd(&L.forces[3 * T.iatom + i], scale * v);
+          else if (i < 6)
+            atomicAdd(&L.forces[3 * T.jatom + i - 3], scale * v);
+          else
+            atomicAdd(&L.virial[i - 6], scale * v);
+        }
+      }
     }
-    __syncthreads();
-    if (t < nred) {
-      double v = 0.0;
-      for (int w = 0; w < kHabThreads / 32; w++)
-        v += s_red[w][t];
-      const double scale = (T0.iatom == T0.jatom) ? 1.0 : 2.0;
-      if (t < 3)
-        atomicAdd(&L.forces[3 * T0.iatom + t], scale * v);
-      else if (t < 6)
-        atomicAdd(&L.forces[3 * T0.jatom + t - 3], scale * v);
-      else
-        atomicAdd(&L.virial[t - 6], scale * v);
-    }
+    __syncwarp();
   }
 }
-
 
 // ---------------------------------------------------------------------------
 // host launchers
@@ -595,10 +578,10 @@ inline void launch_pab_to_coef(const CoefLaunch &L, const int func, const double
   count_launch();
 }
 
-inline void launch_coef_to_hab(const HabLaunch &L, const int max_ncoset_raw,
-                               const int max_block_size, const int dla_max, const int dla_min,
-                               const int dlb_max, const int dlb_min) {
-  if (L.nblocks == 0)
+inline void launch_coef_to_hab(const HabLaunch &L, const int ntasks, const int max_ncoset_raw,
+                               const int dla_max, const int dla_min, const int dlb_max,
+                               const int dlb_min) {
+  if (ntasks == 0)
     return;
   HabDims D;
   D.work = L.max_nsgf_set * max_ncoset_raw;
@@ -607,18 +590,15 @@ inline void launch_coef_to_hab(const HabLaunch &L, const int max_ncoset_raw,
   D.alpha = 3 * (L.max_la_l + 1) * (L.max_lb_l + 1) * (L.max_la_l + L.max_lb_l + 1);
   D.cxyz = ncoset(L.max_la_l + L.max_lb_l);
   D.h = max_ncoset_raw * max_ncoset_raw;
-  D.block = max_block_size;
-  bool block_in_smem = true;
-  if ((size_t)D.total() * sizeof(double) > kSmemBudget) {
-    D.block = 0;
-    block_in_smem = false;
-  }
-  const size_t bytes = (size_t)D.total() * sizeof(double);
-  B200_ASSERT(bytes <= kSmemBudget, "basis too large for the hab kernel");
+  const size_t per_warp = (size_t)D.total() * sizeof(double);
+  B200_ASSERT(per_warp <= kSmemBudget, "basis too large for the hab kernel");
+  const int wpc = (int)std::min<size_t>(4, kSmemBudget / per_warp);
+  const size_t bytes = per_warp * wpc;
   B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)bytes));
-  coef_to_hab_kernel<<<L.nblocks, kHabThreads, bytes, L.stream>>>(L, D, dla_max, dla_min, dlb_max,
-                                                                  dlb_min, block_in_smem);
+  const int grid = std::min((ntasks + wpc - 1) / wpc, 148 * 16);
+  coef_to_hab_kernel<<<grid, 32 * wpc, bytes, L.stream>>>(L, D, ntasks, dla_max, dla_min, dlb_max,
+                                                         dlb_min);
   B200_CHECK(cudaGetLastError());
   count_launch();
 }

@@ -46,7 +46,12 @@ __host__ __device__ inline size_t gen_smem_bytes(const int max_lp, const int max
 template <bool COLLOCATE>
 __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L) {
   extern __shared__ double smem[];
+  __shared__ unsigned s_orb[kOrbEntries];
   const int tid = threadIdx.x;
+  if (!COLLOCATE) {
+    stage_orb_table(s_orb, tid, kGenThreads);
+    __syncthreads();
+  }
   const int itask = L.task_ids[blockIdx.x];
   const TaskDev &T = L.tasks[itask];
   const int lp = T.la_max + T.lb_max + L.dl, lp1 = lp + 1, nc = ncoset(lp);
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
       // ---- phase A': fold the row sums into the coefficients ----------------
       if (nc <= kGenThreads) {
         if (my_g < ngroups) {
-          const Orb o = orb_of(my_c);
+          const Orb o = orb_of(s_orb, my_c);
           for (int r = my_g; r < nr; r += ngroups) {
             if (s_info[4 * r] < 0)
               continue;
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
           const int c = tid + m * kGenThreads;
           if (c >= nc)
             break;
-          const Orb o = orb_of(c);
+          const Orb o = orb_of(s_orb, c);
           for (int r = 0; r < nr; r++) {
             if (s_info[4 * r] < 0)
               continue;

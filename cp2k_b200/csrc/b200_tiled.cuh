@@ -43,7 +43,7 @@ constexpr int kTiledWarps = kTiledThreads / 32;
 constexpr int kTiledMaxLp = 6;                // beyond: generic kernels
 constexpr int kTiledMaxN = 30;                // max discretised radius index (sphere tables <= ~40 KB)
 constexpr int kLpBuckets = kTiledMaxLp + 1;
-constexpr int kItemPairs = 1024;              // pairs per work item (upper bound)
+constexpr int kItemPairs = 512;               // pairs per work item (upper bound)
 // lp classes (by lp0 = la_max + lb_max): separate kernel instantiations keep the
 // code of each kernel small (instruction cache!) and the registers low
 constexpr int kNumClasses = 3;
@@ -97,6 +97,7 @@ struct TiledLevel {
   TTask *d_ttasks = nullptr;
   TPair *d_pairs = nullptr;
   TWork *d_work = nullptr;
+  int *d_counters = nullptr;         // one per (direction, class)
   KTabHeader *d_khead = nullptr;
   signed char *d_ktab = nullptr;
   double *d_etab = nullptr;          // [ttask][3][P]
@@ -104,6 +105,8 @@ struct TiledLevel {
   void release() {
     cudaFree(d_ttasks), cudaFree(d_pairs), cudaFree(d_work), cudaFree(d_khead), cudaFree(d_ktab);
     cudaFree(d_etab);
+    cudaFree(d_counters);
+    d_counters = nullptr;
     for (auto &p : d_class_task_ids) {
       cudaFree(p);
       p = nullptr;
@@ -437,9 +440,10 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
         work.push_back(W);
       }
     }
-    // longest first; the warps of a CTA then get items of similar length
-    std::stable_sort(work.begin() + w0, work.end(),
-                     [](const TWork &a, const TWork &b) { return (a.last - a.first) > (b.last - b.first); });
+    // Items stay in spatial (block) order: warps that run concurrently then work on
+    // neighbouring blocks and share the tasks' table rows through L2.  They are
+    // handed out dynamically (atomic counter), so no size sorting is needed.
+    (void)w0;
   }
   tl.class_work_first[kNumClasses] = (int)work.size();
   // TaskDev ids per class (for calls whose l growth pushes a class out of the tiled range)
@@ -453,6 +457,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   }
   tl.nwork = (int)work.size();
   up(&tl.d_work, work);
+  B200_CHECK(cudaMalloc((void **)&tl.d_counters, 2 * kNumClasses * sizeof(int)));
   B200_CHECK(cudaStreamSynchronize(s));
   cudaFree(d_temp), cudaFree(d_count), cudaFree(d_start);
 }
@@ -469,6 +474,7 @@ struct TiledArgs {
   const TPair *pairs;
   const TWork *work;         // work items of ONE lp class
   int nwork;
+  int *counter;              // dynamic work distribution (zeroed before the launch)
   const KTabHeader *khead;
   const signed char *ktab;
   int ktab_bytes, max_n;
@@ -709,8 +715,14 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kern
     ((int4 *)s_ktab)[q] = ((const int4 *)A.ktab)[q];
   __syncthreads();  // the only CTA-wide barrier
 
-  // persistent warps: work items (sorted longest first) are dealt round-robin
-  for (int iw = blockIdx.x * kTiledWarps + warp; iw < A.nwork; iw += gridDim.x * kTiledWarps) {
+  // persistent warps: work items are handed out in spatial order
+  for (;;) {
+  int iw = 0;
+  if (lane == 0)
+    iw = atomicAdd(A.counter, 1);
+  iw = __shfl_sync(0xffffffffu, iw, 0);
+  if (iw >= A.nwork)
+    break;
   const TWork W = A.work[iw];
   const int vx = min(kBX, A.nx - W.x0), vy = min(kBY, A.ny - W.y0), vz = min(kBZ, A.nz - W.z0);
   const int li = lane & 7, lj = lane >> 3;  // my columns: (li, lj) and (li, lj + 4)
@@ -874,7 +886,10 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
   A.hx = L.level.dh[0], A.hy = L.level.dh[4], A.hz = L.level.dh[8];
   A.dl = L.dl;
   unsigned leftover = 0u;
+  B200_CHECK(cudaMemsetAsync(tl.d_counters + (COLLOCATE ? 0 : kNumClasses), 0, kNumClasses * sizeof(int),
+                             L.stream));
   for (int cls = 0; cls < kNumClasses; cls++) {
+    A.counter = tl.d_counters + (COLLOCATE ? 0 : kNumClasses) + cls;
     A.work = tl.d_work + tl.class_work_first[cls];
     A.nwork = tl.class_work_first[cls + 1] - tl.class_work_first[cls];
     if (A.nwork == 0)

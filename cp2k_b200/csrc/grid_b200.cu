@@ -160,10 +160,22 @@ struct TaskList {
   int max_nsgf_set = 1, max_ncoset_raw = 1, max_la = 0, max_lb = 0, maxco = 1;
   int max_block_size = 1;
   size_t pab_len = 0;
+  std::vector<cudaStream_t> level_streams;   // the levels' grid kernels run concurrently
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_join;
   double stats[16] = {0};
   bool stats_ready = false;
 
   void release() {
+    for (auto st : level_streams)
+      cudaStreamDestroy(st);
+    level_streams.clear();
+    for (auto ev : ev_join)
+      cudaEventDestroy(ev);
+    ev_join.clear();
+    if (ev_fork)
+      cudaEventDestroy(ev_fork);
+    ev_fork = nullptr;
     d_tasks.release(), d_sphi.release(), d_iota.release(), d_generic_ids.release();
     d_block_task_ids.release(), d_block_first.release();
     for (auto &b : d_coef_off)
@@ -525,6 +537,13 @@ static void build_task_list(
   }
   tl.generic_first[nlevels] = (int)tl.h_generic_ids.size();
   tl.d_generic_ids.upload(tl.h_generic_ids, s);
+  tl.level_streams.resize(nlevels);
+  tl.ev_join.resize(nlevels);
+  B200_CHECK(cudaEventCreateWithFlags(&tl.ev_fork, cudaEventDisableTiming));
+  for (int l = 0; l < nlevels; l++) {
+    B200_CHECK(cudaStreamCreateWithFlags(&tl.level_streams[l], cudaStreamNonBlocking));
+    B200_CHECK(cudaEventCreateWithFlags(&tl.ev_join[l], cudaEventDisableTiming));
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -679,6 +698,10 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
                        tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
   }
 
+  // The levels are independent: fork one stream per level, join afterwards.
+  // T_COLLOCATE spans fork..join, i.e. all grid kernels of this call.
+  ScopedTimer *tm_grid = new ScopedTimer(T_COLLOCATE, s);
+  B200_CHECK(cudaEventRecord(tl.ev_fork, s));
   for (int l = 0; l < nlevels; l++) {
     const LevelDev &L = tl.levels[l];
     LevelInfo &li = tl.linfo[l];
@@ -690,17 +713,15 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
       tl.d_grids[l].ensure(npts);
       d_grid = tl.d_grids[l].p;
     }
-    {
-      ScopedTimer tm(T_MEMSET, s);
-      B200_CHECK(cudaMemsetAsync(d_grid, 0, npts * sizeof(double), s));
-    }
+    cudaStream_t ls = tl.level_streams[l];
+    B200_CHECK(cudaStreamWaitEvent(ls, tl.ev_fork, 0));
+    B200_CHECK(cudaMemsetAsync(d_grid, 0, npts * sizeof(double), ls));
     const bool force_generic = (g_variant == 1);
     GridLaunch GL;
     GL.tasks = tl.d_tasks.p, GL.level = L, GL.dl = dl;
     GL.coef_offsets = tl.d_coef_off[dl].p, GL.coef = tl.d_coef.p, GL.grid = d_grid;
-    GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = s;
+    GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = ls;
     {
-      ScopedTimer tm(T_COLLOCATE, s);
       if (force_generic || !tiled_supports(li.tiled, li.max_lp0 + dl)) {
         GL.task_ids = tl.d_iota.p + li.first, GL.ntasks = li.last - li.first;
         launch_generic(GL, true);
@@ -715,12 +736,14 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
           }
       }
     }
-    if (!resident) {
-      ScopedTimer tm(T_D2H, s);
+    if (!resident)
       B200_CHECK(cudaMemcpyAsync(grids[l]->host_buffer, d_grid, npts * sizeof(double),
-                                 cudaMemcpyDeviceToHost, s));
-    }
+                                 cudaMemcpyDeviceToHost, ls));
+    B200_CHECK(cudaEventRecord(tl.ev_join[l], ls));
   }
+  for (int l = 0; l < nlevels; l++)
+    B200_CHECK(cudaStreamWaitEvent(s, tl.ev_join[l], 0));
+  delete tm_grid;
   if (!g_device_resident)
     B200_CHECK(cudaStreamSynchronize(s));
 }
@@ -770,27 +793,29 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
     B200_CHECK(cudaMemsetAsync(tl.d_coef.p, 0, tl.coef_total[dl] * sizeof(double), s));
   }
 
+  ScopedTimer *tm_grid = new ScopedTimer(T_INTEGRATE, s);
+  B200_CHECK(cudaEventRecord(tl.ev_fork, s));
   for (int l = 0; l < nlevels; l++) {
     const LevelDev &L = tl.levels[l];
     LevelInfo &li = tl.linfo[l];
     const size_t npts = (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2];
     B200_ASSERT(grids[l]->size >= npts * sizeof(double), "grid buffer smaller than npts_local");
+    cudaStream_t ls = tl.level_streams[l];
+    B200_CHECK(cudaStreamWaitEvent(ls, tl.ev_fork, 0));
     double *d_grid = use_caller_device(grids[l]) ? grids[l]->device_buffer : nullptr;
     if (!(g_device_resident && d_grid != nullptr)) {
       if (d_grid == nullptr) {
         tl.d_grids[l].ensure(npts);
         d_grid = tl.d_grids[l].p;
       }
-      ScopedTimer tm(T_H2D, s);
       B200_CHECK(cudaMemcpyAsync(d_grid, grids[l]->host_buffer, npts * sizeof(double),
-                                 cudaMemcpyHostToDevice, s));
+                                 cudaMemcpyHostToDevice, ls));
     }
     const bool force_generic = (g_variant == 1);
     GridLaunch GL;
     GL.tasks = tl.d_tasks.p, GL.level = L, GL.dl = dl;
     GL.coef_offsets = tl.d_coef_off[dl].p, GL.coef = tl.d_coef.p, GL.grid = d_grid;
-    GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = s;
-    ScopedTimer tm(T_INTEGRATE, s);
+    GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = ls;
     if (force_generic || !tiled_supports(li.tiled, li.max_lp0 + dl)) {
       GL.task_ids = tl.d_iota.p + li.first, GL.ntasks = li.last - li.first;
       launch_generic(GL, false);
@@ -804,7 +829,11 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
           launch_generic(GL, false);
         }
     }
+    B200_CHECK(cudaEventRecord(tl.ev_join[l], ls));
   }
+  for (int l = 0; l < nlevels; l++)
+    B200_CHECK(cudaStreamWaitEvent(s, tl.ev_join[l], 0));
+  delete tm_grid;
 
   const double *d_pab = nullptr;
   if (do_f) {
@@ -846,7 +875,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   HL.max_la_l = tl.max_la + dla_max, HL.max_lb_l = tl.max_lb + dlb_max, HL.stream = s;
   {
     ScopedTimer tm(T_COEF2HAB, s);
-    launch_coef_to_hab(HL, tl.max_ncoset_raw, tl.max_block_size, dla_max, dla_min, dlb_max, dlb_min);
+    launch_coef_to_hab(HL, tl.ntasks, tl.max_ncoset_raw, dla_max, dla_min, dlb_max, dlb_min);
   }
   if (!hab_resident) {
     ScopedTimer tm(T_D2H, s);
