@@ -126,7 +126,9 @@ def bench_config(wl, args, extra=None):
                        + ("+forces+virial" if args.forces else ""),
            "ntasks": wl.ntasks, "nblocks": wl.nblocks, "natoms": wl.natoms,
            "l2": "per-step working set (task records + P/H blocks + grids > 0.5 GB) exceeds the 126 MB L2",
-           "parallelism": f"blocks/tasks split over {args.gpus} GPU(s), replicated grids, NCCL all-reduce"}
+           "parallelism": (f"z-slab rs_grids over {args.gpus} GPU(s), NCCL halo sum/fill"
+                           if getattr(args, "decomp", "blocks") == "slab" and args.gpus > 1 else
+                           f"blocks/tasks split over {args.gpus} GPU(s), replicated grids, NCCL all-reduce")}
     if extra:
         cfg.update(extra)
     return cfg
@@ -213,6 +215,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--decomp", default="blocks", choices=["blocks", "slab"],
+                    help="multi-GPU decomposition: matrix blocks + replicated grids + all-reduce (default), "
+                         "or z-slab rs_grids + NCCL halo sum/fill (cp2k_b200/rsgrid.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -240,7 +245,14 @@ def main():
     lib.set_kernel_variant(args.variant)
 
     wl_full = build_h2o_workload(args.workload)
-    wl = split_blocks(wl_full, world, rank)
+    slab_levels = None
+    if args.decomp == "slab" and world > 1:
+        from cp2k_b200 import rsgrid
+
+        slab_levels = rsgrid.make_slab_levels(wl_full, world)
+        wl = rsgrid.local_workload(wl_full, slab_levels, rank, world)
+    else:
+        wl = split_blocks(wl_full, world, rank)
     tl = wl.create(lib)
     st = lib.stats(tl)
     flops_local = st["flops_collocate"] + st["flops_integrate"]
@@ -260,12 +272,26 @@ def main():
     forces = np.zeros((wl.natoms, 3)) if args.forces else None
     virial = np.zeros((3, 3)) if args.forces else None
 
+    def exchange(gs):
+        """The exchange step between collocate and integrate."""
+        if world == 1:
+            return
+        if slab_levels is None:
+            for g in gs:
+                dist.all_reduce(g.device)
+            return
+        for lay, sl, g in zip(wl.layouts, slab_levels, gs):
+            n = lay.npts_local
+            t = g.device[: int(n[0]) * int(n[1]) * int(n[2])].view(int(n[2]), int(n[1]), int(n[0]))
+            rsgrid.halo_sum(t, sl, rank, world, dist)   # density: halos -> owners
+            rsgrid.halo_fill(t, sl, rank, world, dist)  # potential: owners -> halos
+
     def step_resident():
         tl.collocate(100, pab, grids)
-        if world > 1:
-            for g in grids:
-                dist.all_reduce(g.device)
+        exchange(grids)
         tl.integrate(False, pab if args.forces else None, grids, hab, forces, virial)
+        if slab_levels is not None:
+            dist.all_reduce(hab.device)  # a block's tasks may live on several slabs
 
     def barrier():
         if world > 1:
@@ -332,8 +358,8 @@ def main():
     def step_e2e():
         tl.collocate(100, pab_e, grids_e)  # H2D pab, kernels, D2H grids
         if world > 1:
+            exchange(grids_e)
             for g in grids_e:
-                dist.all_reduce(g.device)
                 g.host[:] = g.device.cpu().numpy()[: g.host.size]
         tl.integrate(False, pab_e if args.forces else None, grids_e, hab_e, forces, virial)  # H2D grids, D2H hab
 

@@ -1,0 +1,234 @@
+"""z-slab distribution of the real-space grids over the ranks (GPUs) of one
+box, with the halo exchange that brackets the grid hot path.
+
+Restates, for the 1-D slab case, CP2K's rs_grid layer
+(`src/pw/realspace_grid_types.F`):
+
+  descriptor      :285-329 (group_dim choice; for cubic grids and <= 8 ranks a
+                  1-D slab wins), :413-415 (get_limit), :514-519 (local bounds =
+                  owned +- border), :266-267 (border = (max cube width + 1) / 2)
+  task ownership  src/task_list_methods.F:2711-2726 (rank owning the cube centre)
+  halo sum        realspace_grid_types.F:988-1204 (after collocate: halo planes
+                  are sent to their owners and ADDED, n_shifts rounds when the
+                  border is wider than a slab)
+  halo fill       :1677-1893 (before integrate: owned planes are copied into the
+                  neighbours' halos)
+  local layout    src/grid/grid_api.F:501-547 (npts_local, shift_local,
+                  border_width as handed to grid_create_task_list)
+
+The exchange is expressed with `torch.distributed` point-to-point ops on
+contiguous z-plane ranges (z is the slowest grid index), so the same code runs
+over NCCL/NVLink on GPUs and over gloo in the CPU tests.  Levels whose slab plus
+two borders would not fit into the global grid stay replicated, exactly like the
+reference refuses such layouts (:305-314).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .grid_api import GridLayout
+from .workload import Workload
+
+
+def get_limit(n: int, nparts: int, part: int) -> Tuple[int, int]:
+    """Owned index range [lo, hi) of `part` (cf. get_limit, src/common/util.F):
+    the first n % nparts parts get one extra plane."""
+    base, extra = divmod(n, nparts)
+    lo = part * base + min(part, extra)
+    return lo, lo + base + (1 if part < extra else 0)
+
+
+@dataclass
+class SlabLevel:
+    distributed: bool
+    npts_global: np.ndarray
+    border: int
+    owned: List[Tuple[int, int]]       # per rank: owned global z-planes [lo, hi)
+
+    def local_planes(self, rank: int) -> np.ndarray:
+        """Global z index of every local plane of `rank` (halo included)."""
+        nz = int(self.npts_global[2])
+        if not self.distributed:
+            return np.arange(nz)
+        lo, hi = self.owned[rank]
+        return np.arange(lo - self.border, hi + self.border) % nz
+
+
+def cube_halfwidth(wl: Workload, level: int) -> int:
+    """Largest cube half-width (grid points, z) on a level, from the discretised
+    radius rule of src/grid/ref/grid_ref_collint.h:237-245."""
+    lay = wl.layouts[level]
+    sel = wl.tasks["level_list"] == level + 1
+    if not np.any(sel):
+        return 1
+    h = np.array([lay.dh[0][0], lay.dh[1][1], lay.dh[2][2]])
+    drmin = h.min()
+    disr = drmin * np.maximum(1.0, np.ceil(wl.tasks["radius_list"][sel] / drmin))
+    lb = np.ceil(-1e-8 - disr.max() * lay.dh_inv[2][2])
+    return int(1 - lb)
+
+
+def make_slab_levels(wl: Workload, world: int) -> List[SlabLevel]:
+    levels = []
+    for ilev, lay in enumerate(wl.layouts):
+        npts = np.asarray(lay.npts_global, dtype=np.int64)
+        border = cube_halfwidth(wl, ilev) + 1
+        owned = [get_limit(int(npts[2]), world, r) for r in range(world)]
+        thickest = max(hi - lo for lo, hi in owned)
+        distributed = wl.orthorhombic and world > 1 and thickest + 2 * border <= int(npts[2])
+        levels.append(SlabLevel(distributed, npts, border, owned))
+    return levels
+
+
+def _exponents(wl: Workload, kinds, isets, ipgfs) -> np.ndarray:
+    out = np.zeros(kinds.shape[0])
+    for k, b in enumerate(wl.basis_sets):
+        m = kinds == k
+        out[m] = b.zet[isets[m], ipgfs[m]]
+    return out
+
+
+def local_workload(wl: Workload, levels: Sequence[SlabLevel], rank: int, world: int) -> Workload:
+    """The task list and grid layouts of one rank.
+
+    Distributed levels: a task belongs to the rank owning the z-plane of its cube
+    centre (the halo is wide enough for the whole cube).  Replicated levels: tasks
+    are dealt to ranks by matrix block (every rank holds the full grid)."""
+    t = wl.tasks
+    keep = np.zeros(wl.ntasks, dtype=bool)
+    layouts = []
+    for ilev, (lay, sl) in enumerate(zip(wl.layouts, levels)):
+        sel = np.nonzero(t["level_list"] == ilev + 1)[0]
+        if sl.distributed:
+            ia = t["iatom_list"][sel] - 1
+            ja = t["jatom_list"][sel] - 1
+            zeta = _exponents(wl, wl.atom_kinds[ia] - 1, t["iset_list"][sel] - 1, t["ipgf_list"][sel] - 1)
+            zetb = _exponents(wl, wl.atom_kinds[ja] - 1, t["jset_list"][sel] - 1, t["jpgf_list"][sel] - 1)
+            rp_z = wl.atom_positions[ia, 2] + zetb / (zeta + zetb) * t["rab_list"][sel, 2]
+            nz = int(sl.npts_global[2])
+            centre = np.floor(lay.dh_inv[2][2] * rp_z).astype(np.int64) % nz
+            lo, hi = sl.owned[rank]
+            keep[sel[(centre >= lo) & (centre < hi)]] = True
+            nloc = np.array(lay.npts_global, dtype=np.int32)
+            nloc[2] = (hi - lo) + 2 * sl.border
+            shift = np.array([0, 0, lo - sl.border], dtype=np.int32)
+            layouts.append(GridLayout(lay.npts_global, nloc, shift, np.array([0, 0, sl.border], np.int32),
+                                      lay.dh, lay.dh_inv))
+        else:
+            keep[sel[(t["block_num_list"][sel] - 1) % world == rank]] = True
+            layouts.append(lay)
+    sub = wl.subset(keep)
+    sub.layouts = layouts
+    return sub
+
+
+# ----------------------------------------------------------------------------
+# halo exchange
+# ----------------------------------------------------------------------------
+def _segments(planes: np.ndarray) -> List[Tuple[int, int]]:
+    """Split a sorted array of local plane indices into contiguous [a, b) runs."""
+    if planes.size == 0:
+        return []
+    cuts = np.nonzero(np.diff(planes) != 1)[0] + 1
+    return [(int(s[0]), int(s[-1]) + 1) for s in np.split(planes, cuts)]
+
+
+def _exchange_plan(sl: SlabLevel, world: int):
+    """For every ordered pair (src, dst): the local plane indices of src's HALO
+    that dst OWNS, and the matching local plane indices on dst."""
+    plan = {}
+    for src in range(world):
+        gsrc = sl.local_planes(src)
+        lo_s, hi_s = sl.owned[src]
+        nown = hi_s - lo_s
+        halo_local = np.concatenate([np.arange(0, sl.border), np.arange(sl.border + nown, gsrc.size)])
+        for dst in range(world):
+            if dst == src:
+                continue
+            lo_d, hi_d = sl.owned[dst]
+            g = gsrc[halo_local]
+            m = (g >= lo_d) & (g < hi_d)
+            if not np.any(m):
+                continue
+            src_idx = halo_local[m]
+            dst_idx = g[m] - lo_d + sl.border
+            order = np.argsort(src_idx, kind="stable")
+            plan[(src, dst)] = (src_idx[order], dst_idx[order])
+    return plan
+
+
+def _p2p(ops, dist):
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def halo_sum(grid, sl: SlabLevel, rank: int, world: int, dist) -> None:
+    """After collocate: add every rank's halo planes into their owners
+    (realspace_grid_types.F:988-1204).  `grid` is the rank's local grid as a torch
+    tensor of shape [nz_local, ny, nx] (CPU for gloo, CUDA for nccl).  Replicated
+    levels are summed with one all-reduce (:763-825)."""
+    import torch
+
+    if not sl.distributed:
+        if world > 1:
+            dist.all_reduce(grid)
+        return
+    plan = _exchange_plan(sl, world)
+    ops, recvs = [], []
+    for (src, dst), (src_idx, dst_idx) in sorted(plan.items()):
+        if src == rank:
+            for a, b in _segments(src_idx):
+                ops.append(dist.P2POp(dist.isend, grid[a:b].contiguous(), dst))
+        if dst == rank:
+            for (a, b) in _segments(src_idx):  # same segmentation as the sender
+                n = b - a
+                buf = torch.empty((n,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
+                first = int(dst_idx[np.searchsorted(src_idx, a)])
+                ops.append(dist.P2POp(dist.irecv, buf, src))
+                recvs.append((first, n, buf, dst_idx[np.searchsorted(src_idx, a): np.searchsorted(src_idx, a) + n]))
+    _p2p(ops, dist)
+    for first, n, buf, didx in recvs:
+        # destination planes of one sender segment are contiguous unless they wrap
+        for k, d in enumerate(didx):
+            grid[int(d)] += buf[k]
+    # the halo has been handed over: zero it so that a later sum is idempotent
+    lo, hi = sl.owned[rank]
+    grid[: sl.border] = 0
+    grid[sl.border + (hi - lo):] = 0
+
+
+def halo_fill(grid, sl: SlabLevel, rank: int, world: int, dist) -> None:
+    """Before integrate: copy the owners' planes into every rank's halo
+    (realspace_grid_types.F:1677-1893)."""
+    import torch
+
+    if not sl.distributed:
+        return
+    plan = _exchange_plan(sl, world)  # (halo holder, owner)
+    ops, recvs = [], []
+    for (holder, owner), (halo_idx, own_idx) in sorted(plan.items()):
+        if owner == rank:
+            for a, b in _segments(halo_idx):
+                i0 = np.searchsorted(halo_idx, a)
+                rows = own_idx[i0: i0 + (b - a)]
+                ops.append(dist.P2POp(dist.isend, grid[torch.as_tensor(rows, device=grid.device)].contiguous(),
+                                      holder))
+        if holder == rank:
+            for a, b in _segments(halo_idx):
+                buf = torch.empty((b - a,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
+                ops.append(dist.P2POp(dist.irecv, buf, owner))
+                recvs.append((a, b, buf))
+    _p2p(ops, dist)
+    for a, b, buf in recvs:
+        grid[a:b] = buf
+
+
+def owned_view(grid, sl: SlabLevel, rank: int):
+    if not sl.distributed:
+        return grid
+    lo, hi = sl.owned[rank]
+    return grid[sl.border: sl.border + (hi - lo)]

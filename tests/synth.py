@@ -15,6 +15,7 @@ from typing import List
 import numpy as np
 
 from cp2k_b200.grid_api import BasisSet, GridLayout, OffloadBuffer
+from cp2k_b200.workload import Workload
 
 
 def ncoset(l):
@@ -42,38 +43,6 @@ def random_basis(rng, sets, zet_range=(0.15, 3.0)) -> BasisSet:
             block[:, p * ncoset(hi): p * ncoset(hi) + ncoset(lo - 1)] = 0.0
         sphi[first_sgf[i] - 1: first_sgf[i] - 1 + ns, : n * ncoset(hi)] = block
     return BasisSet(lmin, lmax, npgf, nsgf_set, first_sgf, sphi, zet)
-
-
-@dataclass
-class Workload:
-    orthorhombic: bool
-    natoms: int
-    atom_positions: np.ndarray
-    atom_kinds: np.ndarray
-    basis_sets: List[BasisSet]
-    layouts: List[GridLayout]
-    block_offsets: np.ndarray
-    tasks: dict
-    pab_len: int
-    meta: dict = field(default_factory=dict)
-
-    @property
-    def ntasks(self):
-        return int(self.tasks["level_list"].shape[0])
-
-    def create(self, lib):
-        return lib.create_task_list(
-            orthorhombic=self.orthorhombic, natoms=self.natoms, block_offsets=self.block_offsets,
-            atom_positions=self.atom_positions, atom_kinds=self.atom_kinds, basis_sets=self.basis_sets,
-            layouts=self.layouts, **self.tasks)
-
-    def new_grids(self, make=OffloadBuffer):
-        return [make(l.npts_local_total) for l in self.layouts]
-
-    def random_pab(self, seed=1, make=OffloadBuffer):
-        buf = make(self.pab_len)
-        buf.host[:] = np.random.default_rng(seed).normal(size=self.pab_len)
-        return buf
 
 
 def make_cell(rng, edge, orthorhombic, skew=0.12):

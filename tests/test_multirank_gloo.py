@@ -1,0 +1,118 @@
+"""World-size-2 tests of the multi-GPU host logic on CPU (gloo): the task split,
+the z-slab rs_grid layouts and the halo sum / halo fill, with the oracle playing
+the role of the per-rank backend.  The same code drives NCCL on the GPU box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, mode, result_file):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cp2k_b200.grid_api import OffloadBuffer
+    from cp2k_b200 import rsgrid
+    from oracle import pyref
+    from synth import make_workload
+    import bench
+
+    ora = pyref.load_oracle()
+    wl = make_workload(seed=41, natoms=5, max_tasks=500, edge=(9.0, 10.0, 16.0),
+                       npts_list=((40, 45, 72), (20, 24, 36)))
+    pab = wl.random_pab(2)
+    # full reference result (every rank computes it; small)
+    tl = wl.create(ora)
+    full = wl.new_grids()
+    tl.collocate(100, pab, full)
+    hab_full = OffloadBuffer(wl.pab_len)
+    tl.integrate(False, None, full, hab_full)
+    tl.free()
+
+    errs = {}
+    if mode == "replicated":
+        mine = bench.split_blocks(wl, world, rank)
+        counts = torch.tensor([mine.ntasks], dtype=torch.int64)
+        dist.all_reduce(counts)
+        assert int(counts) == wl.ntasks  # a partition: nothing lost, nothing duplicated
+        tl = mine.create(ora)
+        grids = mine.new_grids()
+        tl.collocate(100, pab, grids)
+        for g in grids:
+            t = torch.from_numpy(g.host)
+            dist.all_reduce(t)
+        errs["grid"] = max(float(np.abs(g.host - f.host).max()) for g, f in zip(grids, full))
+        hab = OffloadBuffer(wl.pab_len)
+        tl.integrate(False, None, grids, hab)
+        t = torch.from_numpy(hab.host)
+        dist.all_reduce(t)
+        errs["hab"] = float(np.abs(hab.host - hab_full.host).max())
+        tl.free()
+    else:
+        levels = rsgrid.make_slab_levels(wl, world)
+        assert any(l.distributed for l in levels)
+        mine = rsgrid.local_workload(wl, levels, rank, world)
+        counts = torch.tensor([mine.ntasks], dtype=torch.int64)
+        dist.all_reduce(counts)
+        assert int(counts) == wl.ntasks
+        tl = mine.create(ora)
+        grids = mine.new_grids()
+        tl.collocate(100, pab, grids)
+        gerr = 0.0
+        for lay, sl, g, f in zip(mine.layouts, levels, grids, full):
+            n = lay.npts_local
+            t = torch.from_numpy(g.host).view(int(n[2]), int(n[1]), int(n[0]))
+            rsgrid.halo_sum(t, sl, rank, world, dist)
+            ref = f.host.reshape(int(sl.npts_global[2]), int(n[1]), int(n[0]))
+            planes = sl.local_planes(rank)
+            own = rsgrid.owned_view(t, sl, rank).numpy()
+            if sl.distributed:
+                lo, hi = sl.owned[rank]
+                gerr = max(gerr, float(np.abs(own - ref[lo:hi]).max()))
+                # halo fill: afterwards every local plane equals the global one
+                rsgrid.halo_fill(t, sl, rank, world, dist)
+                gerr = max(gerr, float(np.abs(t.numpy() - ref[planes]).max()))
+            else:
+                gerr = max(gerr, float(np.abs(own - ref).max()))
+        errs["grid"] = gerr
+        hab = OffloadBuffer(wl.pab_len)
+        tl.integrate(False, None, grids, hab)  # grids now hold the filled potential
+        t = torch.from_numpy(hab.host)
+        dist.all_reduce(t)
+        errs["hab"] = float(np.abs(hab.host - hab_full.host).max())
+        tl.free()
+    if rank == 0:
+        np.save(result_file, np.array([errs["grid"], errs["hab"]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["replicated", "slab"])
+def test_two_ranks(mode, tmp_path):
+    port = 29500 + (os.getpid() % 400) + (0 if mode == "replicated" else 401)
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
+    grid_err, hab_err = np.load(out)
+    assert grid_err < 1e-11
+    assert hab_err < 1e-10
+
+
+def test_get_limit_partitions():
+    from cp2k_b200.rsgrid import get_limit
+
+    for n in (40, 70, 126, 200):
+        for parts in (1, 2, 3, 8):
+            spans = [get_limit(n, parts, p) for p in range(parts)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
