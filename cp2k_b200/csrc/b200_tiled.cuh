@@ -563,26 +563,19 @@ template <int LP> struct IntegrateReduce {
   }
 };
 
-// The 16 planes of a block, entered at the first plane any lane needs and left
-// after the last one (both warp-uniform): no per-plane range checks.
+// The 16 planes of a block in pairs (two independent FMA chains per column keep
+// the FP64 pipe fed), entered at the first pair any lane needs and left after the
+// last one (both warp-uniform); planes outside a lane's range are masked.
 #define B200_PLANES(BODY)                                                      \
-  switch (wlo) {                                                               \
-  case 0: BODY(0) if (whi == 0) break;                                         \
-  case 1: BODY(1) if (whi == 1) break;                                         \
-  case 2: BODY(2) if (whi == 2) break;                                         \
-  case 3: BODY(3) if (whi == 3) break;                                         \
-  case 4: BODY(4) if (whi == 4) break;                                         \
-  case 5: BODY(5) if (whi == 5) break;                                         \
-  case 6: BODY(6) if (whi == 6) break;                                         \
-  case 7: BODY(7) if (whi == 7) break;                                         \
-  case 8: BODY(8) if (whi == 8) break;                                         \
-  case 9: BODY(9) if (whi == 9) break;                                         \
-  case 10: BODY(10) if (whi == 10) break;                                      \
-  case 11: BODY(11) if (whi == 11) break;                                      \
-  case 12: BODY(12) if (whi == 12) break;                                      \
-  case 13: BODY(13) if (whi == 13) break;                                      \
-  case 14: BODY(14) if (whi == 14) break;                                      \
-  default: BODY(15)                                                            \
+  switch (wlo >> 1) {                                                          \
+  case 0: BODY(0) BODY(1) if (whi <= 1) break;                                 \
+  case 1: BODY(2) BODY(3) if (whi <= 3) break;                                 \
+  case 2: BODY(4) BODY(5) if (whi <= 5) break;                                 \
+  case 3: BODY(6) BODY(7) if (whi <= 7) break;                                 \
+  case 4: BODY(8) BODY(9) if (whi <= 9) break;                                 \
+  case 5: BODY(10) BODY(11) if (whi <= 11) break;                              \
+  case 6: BODY(12) BODY(13) if (whi <= 13) break;                              \
+  default: BODY(14) BODY(15)                                                   \
   }
 
 // One (pair, warp) step.  `ws` is this warp's scratch: [32 entries][LP+1]
