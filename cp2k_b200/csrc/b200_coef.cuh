@@ -236,8 +236,8 @@ __device__ inline void make_alpha(const TaskDev &T, const int la_c,
 // pab_to_coef: one warp per task.
 // ---------------------------------------------------------------------------
 struct CoefDims {
-  int work, raw, cab, alpha, cxyz;  // doubles per warp
-  __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz; }
+  int work, raw, cab, alpha, cxyz, part;  // doubles per warp
+  __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz + part; }
 };
 
 __global__ void __launch_bounds__(128)
@@ -254,6 +254,7 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
   double *s_cab = s_raw + D.raw;
   double *s_alpha = s_cab + D.cab;
   double *s_cxyz = s_alpha + D.alpha;
+  double *s_part = s_cxyz + D.cxyz;
   auto sync = [] { __syncwarp(); };
 
   FuncDesc F;
@@ -310,11 +311,16 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
     const double pref = rscale * T.prefactor;
     const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
     const bool to_cijk = !T.use_ortho;
-    for (int c = lane; c < nc; c += 32) {
-      const Orb k = orb_of(s_orb, c);
+    // two passes so that all lanes work: partial sums per (k, b), then over b
+    const int nbr = n2c - cb_lo;
+    const int cchunk = max(1, D.part / nbr);  // coefficients per pass (scratch size)
+    for (int c0 = 0; c0 < nc; c0 += cchunk) {
+    const int ncc = min(cchunk, nc - c0);
+    for (int q = lane; q < ncc * nbr; q += 32) {
+      const int c = c0 + q / nbr, ib = cb_lo + q % nbr;
+      const Orb k = orb_of(s_orb, c), b = orb_of(s_orb, ib);
       double acc = 0.0;
-      for (int ib = cb_lo; ib < n2c; ib++) {
-        const Orb b = orb_of(s_orb, ib);
+      if (k.l[0] - b.l[0] <= la_c && k.l[1] - b.l[1] <= la_c && k.l[2] - b.l[2] <= la_c) {
         for (int ia = ca_lo; ia < n1c; ia++) {
           const Orb a = orb_of(s_orb, ia);
           if (k.l[0] <= a.l[0] + b.l[0] && k.l[1] <= a.l[1] + b.l[1] &&
@@ -326,10 +332,19 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
           }
         }
       }
+      s_part[q] = acc;
+    }
+    __syncwarp();
+    for (int cc = lane; cc < ncc; cc += 32) {
+      double acc = 0.0;
+      for (int j = 0; j < nbr; j++)
+        acc += s_part[cc * nbr + j];
       if (to_cijk)
-        s_cxyz[c] = acc;
+        s_cxyz[c0 + cc] = acc;
       else
-        out[c] = acc;
+        out[c0 + cc] = acc;
+    }
+    __syncwarp();
     }
     if (to_cijk) {  // lattice-polynomial basis for the general path
       __syncwarp();
@@ -566,6 +581,7 @@ inline void launch_pab_to_coef(const CoefLaunch &L, const int func, const double
   D.cab = ncoset(max_la_c) * ncoset(max_lb_c);
   D.alpha = 3 * (max_la_c + 1) * (max_lb_c + 1) * (max_la_c + max_lb_c + 1);
   D.cxyz = ncoset(max_la_c + max_lb_c);
+  D.part = std::min(ncoset(max_la_c + max_lb_c) * ncoset(max_lb_c), std::max(1024, ncoset(max_lb_c)));
   const size_t per_warp = (size_t)D.total() * sizeof(double);
   B200_ASSERT(per_warp <= kSmemBudget, "basis too large for the coefficient kernel");
   const int wpc = (int)std::min<size_t>(4, kSmemBudget / per_warp);

@@ -17,23 +17,31 @@
 
 #include "../../include/grid_b200.h"
 
+// Failures are loud, as in the reference (assert/abort): message to stderr and,
+// because test runners capture stderr and lose it on abort(), to a log file.
+inline void b200_fatal(const char *what, const char *detail, const char *file, const int line) {
+  fprintf(stderr, "grid_b200: %s (%s) at %s:%d\n", what, detail, file, line);
+  fflush(stderr);
+  const char *path = getenv("GRID_B200_ABORT_LOG");
+  FILE *f = fopen(path ? path : "/tmp/grid_b200_abort.log", "a");
+  if (f) {
+    fprintf(f, "grid_b200: %s (%s) at %s:%d\n", what, detail, file, line);
+    fclose(f);
+  }
+  abort();
+}
+
 #define B200_CHECK(cmd)                                                        \
   do {                                                                         \
     cudaError_t e_ = (cmd);                                                    \
-    if (e_ != cudaSuccess) {                                                   \
-      fprintf(stderr, "grid_b200: CUDA error %s at %s:%d\n",                   \
-              cudaGetErrorString(e_), __FILE__, __LINE__);                     \
-      abort();                                                                 \
-    }                                                                          \
+    if (e_ != cudaSuccess)                                                     \
+      b200_fatal("CUDA error", cudaGetErrorString(e_), __FILE__, __LINE__);    \
   } while (0)
 
 #define B200_ASSERT(cond, msg)                                                 \
   do {                                                                         \
-    if (!(cond)) {                                                             \
-      fprintf(stderr, "grid_b200: %s (%s) at %s:%d\n", msg, #cond, __FILE__,   \
-              __LINE__);                                                       \
-      abort();                                                                 \
-    }                                                                          \
+    if (!(cond))                                                               \
+      b200_fatal(msg, #cond, __FILE__, __LINE__);                              \
   } while (0)
 
 namespace b200 {

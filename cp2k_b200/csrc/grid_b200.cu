@@ -160,6 +160,16 @@ struct TaskList {
   int max_nsgf_set = 1, max_ncoset_raw = 1, max_la = 0, max_lb = 0, maxco = 1;
   int max_block_size = 1;
   size_t pab_len = 0;
+  // host<->device copies of the P/H blocks are pipelined against the coefficient
+  // kernels in chunks of consecutive matrix blocks (needs monotonic offsets)
+  struct Chunk {
+    int t0, t1;        // range in the by-block task order
+    size_t off0;       // first double of the chunk in the block buffers
+  };
+  std::vector<Chunk> chunks;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> ev_chunk;
+  cudaEvent_t ev_copy_done = nullptr;
   std::vector<cudaStream_t> level_streams;   // the levels' grid kernels run concurrently
   cudaEvent_t ev_fork = nullptr;
   std::vector<cudaEvent_t> ev_join;
@@ -176,6 +186,16 @@ struct TaskList {
     if (ev_fork)
       cudaEventDestroy(ev_fork);
     ev_fork = nullptr;
+    for (auto ev : ev_chunk)
+      cudaEventDestroy(ev);
+    ev_chunk.clear();
+    if (ev_copy_done)
+      cudaEventDestroy(ev_copy_done);
+    ev_copy_done = nullptr;
+    if (copy_stream)
+      cudaStreamDestroy(copy_stream);
+    copy_stream = nullptr;
+    chunks.clear();
     d_tasks.release(), d_sphi.release(), d_iota.release(), d_generic_ids.release();
     d_block_task_ids.release(), d_block_first.release();
     for (auto &b : d_coef_off)
@@ -519,6 +539,25 @@ static void build_task_list(
     block_first[b + 1] += block_first[b];
   tl.d_block_task_ids.upload(by_block, s);
   tl.d_block_first.upload(block_first, s);
+  {  // copy/compute pipeline chunks
+    bool monotonic = true;
+    for (int b = 1; b < nblocks; b++)
+      monotonic = monotonic && (block_offsets[b] > block_offsets[b - 1]);
+    const int nchunks = (monotonic && ntasks > 20000) ? 6 : 1;
+    tl.chunks.clear();
+    for (int c = 0; c < nchunks; c++) {
+      const int b0 = (int)((long long)nblocks * c / nchunks);
+      const int b1 = (int)((long long)nblocks * (c + 1) / nchunks);
+      if (b1 > b0)
+        tl.chunks.push_back(TaskList::Chunk{block_first[b0], block_first[b1],
+                                            (c == 0) ? (size_t)0 : (size_t)block_offsets[b0]});
+    }
+    B200_CHECK(cudaStreamCreateWithFlags(&tl.copy_stream, cudaStreamNonBlocking));
+    B200_CHECK(cudaEventCreateWithFlags(&tl.ev_copy_done, cudaEventDisableTiming));
+    tl.ev_chunk.resize(tl.chunks.size());
+    for (auto &ev : tl.ev_chunk)
+      B200_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
 
   tl.h_Tptrs.assign((size_t)nlevels * (kMaxLp + 1), nullptr);
   tl.d_Tptrs.upload(tl.h_Tptrs, s);
@@ -670,32 +709,42 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   ensure_transforms(tl, dl, s);
   tl.d_coef.ensure(tl.coef_total[dl]);
 
-  // density blocks
+  // density blocks -> coefficients.  With host-authoritative buffers the upload
+  // is pipelined chunk-wise against the coefficient kernel.
+  CoefLaunch CL;
+  CL.tasks = tl.d_tasks.p, CL.task_ids = nullptr, CL.ntasks = tl.ntasks;
+  CL.sphi_pool = tl.d_sphi.p, CL.coef_offsets = tl.d_coef_off[dl].p, CL.coef = tl.d_coef.p;
+  CL.cijk_T = tl.d_Tptrs.p, CL.stream = s;
   const double *d_pab = nullptr;
   if (g_device_resident && use_caller_device(pab_blocks)) {
     d_pab = pab_blocks->device_buffer;
+    ScopedTimer tm(T_PAB2COEF, s);
+    launch_pab_to_coef(CL, func, d_pab, tl.max_nsgf_set, tl.max_ncoset_raw,
+                       tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
   } else {
     double *dst = use_caller_device(pab_blocks) ? pab_blocks->device_buffer : nullptr;
     if (dst == nullptr) {
       tl.d_pab.ensure(pab_blocks->size / sizeof(double));
       dst = tl.d_pab.p;
     }
-    {
-      ScopedTimer tm(T_H2D, s);
-      B200_CHECK(cudaMemcpyAsync(dst, pab_blocks->host_buffer, pab_blocks->size,
-                                 cudaMemcpyHostToDevice, s));
-    }
     d_pab = dst;
-  }
-
-  CoefLaunch CL;
-  CL.tasks = tl.d_tasks.p, CL.task_ids = nullptr, CL.ntasks = tl.ntasks;
-  CL.sphi_pool = tl.d_sphi.p, CL.coef_offsets = tl.d_coef_off[dl].p, CL.coef = tl.d_coef.p;
-  CL.cijk_T = tl.d_Tptrs.p, CL.stream = s;
-  {
-    ScopedTimer tm(T_PAB2COEF, s);
-    launch_pab_to_coef(CL, func, d_pab, tl.max_nsgf_set, tl.max_ncoset_raw,
-                       tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
+    const size_t total = pab_blocks->size / sizeof(double);
+    ScopedTimer tm(T_PAB2COEF, s);  // includes the exposed part of the upload
+    B200_CHECK(cudaEventRecord(tl.ev_fork, s));
+    B200_CHECK(cudaStreamWaitEvent(tl.copy_stream, tl.ev_fork, 0));
+    for (size_t c = 0; c < tl.chunks.size(); c++) {
+      const size_t o0 = tl.chunks[c].off0;
+      const size_t o1 = (c + 1 < tl.chunks.size()) ? tl.chunks[c + 1].off0 : total;
+      if (o1 > o0)
+        B200_CHECK(cudaMemcpyAsync(dst + o0, pab_blocks->host_buffer + o0, (o1 - o0) * sizeof(double),
+                                   cudaMemcpyHostToDevice, tl.copy_stream));
+      B200_CHECK(cudaEventRecord(tl.ev_chunk[c], tl.copy_stream));
+      B200_CHECK(cudaStreamWaitEvent(s, tl.ev_chunk[c], 0));
+      CL.task_ids = tl.d_block_task_ids.p + tl.chunks[c].t0;
+      CL.ntasks = tl.chunks[c].t1 - tl.chunks[c].t0;
+      launch_pab_to_coef(CL, func, d_pab, tl.max_nsgf_set, tl.max_ncoset_raw,
+                         tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
+    }
   }
 
   // The levels are independent: fork one stream per level, join afterwards.
@@ -873,14 +922,27 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   HL.virial = do_v ? tl.d_fv.p + (size_t)3 * natoms : nullptr;
   HL.compute_tau = compute_tau, HL.maxco = tl.maxco, HL.max_nsgf_set = tl.max_nsgf_set;
   HL.max_la_l = tl.max_la + dla_max, HL.max_lb_l = tl.max_lb + dlb_max, HL.stream = s;
-  {
+  if (hab_resident) {
     ScopedTimer tm(T_COEF2HAB, s);
     launch_coef_to_hab(HL, tl.ntasks, tl.max_ncoset_raw, dla_max, dla_min, dlb_max, dlb_min);
-  }
-  if (!hab_resident) {
-    ScopedTimer tm(T_D2H, s);
-    B200_CHECK(cudaMemcpyAsync(hab_blocks->host_buffer, d_hab, hab_blocks->size,
-                               cudaMemcpyDeviceToHost, s));
+  } else {
+    // chunk-wise: the download of finished blocks overlaps the remaining kernels
+    const size_t total = hab_blocks->size / sizeof(double);
+    ScopedTimer tm(T_COEF2HAB, s);
+    for (size_t c = 0; c < tl.chunks.size(); c++) {
+      HL.block_task_ids = tl.d_block_task_ids.p + tl.chunks[c].t0;
+      launch_coef_to_hab(HL, tl.chunks[c].t1 - tl.chunks[c].t0, tl.max_ncoset_raw, dla_max, dla_min,
+                         dlb_max, dlb_min);
+      B200_CHECK(cudaEventRecord(tl.ev_chunk[c], s));
+      B200_CHECK(cudaStreamWaitEvent(tl.copy_stream, tl.ev_chunk[c], 0));
+      const size_t o0 = tl.chunks[c].off0;
+      const size_t o1 = (c + 1 < tl.chunks.size()) ? tl.chunks[c + 1].off0 : total;
+      if (o1 > o0)
+        B200_CHECK(cudaMemcpyAsync(hab_blocks->host_buffer + o0, d_hab + o0, (o1 - o0) * sizeof(double),
+                                   cudaMemcpyDeviceToHost, tl.copy_stream));
+    }
+    B200_CHECK(cudaEventRecord(tl.ev_copy_done, tl.copy_stream));
+    B200_CHECK(cudaStreamWaitEvent(s, tl.ev_copy_done, 0));
   }
   if (do_f)
     B200_CHECK(cudaMemcpyAsync(forces, tl.d_fv.p, sizeof(double) * 3 * natoms,
