@@ -240,6 +240,9 @@ struct CoefDims {
   __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz + part; }
 };
 
+// Tasks are tiny: a group of kCoefGroup lanes (half a warp) handles one task, so
+// a warp works on two tasks at once and keeps its lanes busy.
+template <int G>
 __global__ void __launch_bounds__(128)
 pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
                    const CoefDims D) {
@@ -247,15 +250,17 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
   __shared__ unsigned s_orb[kOrbEntries];
   stage_orb_table(s_orb, threadIdx.x, blockDim.x);
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wpc = blockDim.x >> 5;
+  const int lane = threadIdx.x & (G - 1);            // rank within the group
+  const int warp = threadIdx.x / G;                   // group index within the CTA
+  const int wpc = blockDim.x / G;                     // groups per CTA
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
   double *s_work = smem + (size_t)warp * D.total();
   double *s_raw = s_work + D.work;
   double *s_cab = s_raw + D.raw;
   double *s_alpha = s_cab + D.cab;
   double *s_cxyz = s_alpha + D.alpha;
   double *s_part = s_cxyz + D.cxyz;
-  auto sync = [] { __syncwarp(); };
+  auto sync = [gmask] { __syncwarp(gmask); };
 
   FuncDesc F;
   describe_func(func, F);
@@ -269,22 +274,22 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
     const int lp = la_c + lb_c, lp1 = lp + 1, nc = ncoset(lp);
     double *out = L.coef + L.coef_offsets[itask];
     if (T.skip) {
-      for (int c = lane; c < nc; c += 32)
+      for (int c = lane; c < nc; c += G)
         out[c] = 0.0;
       continue;
     }
     decontract_task(T, pab + T.block_offset, L.sphi_pool, s_work, s_raw, lane,
-                    32, sync);
+                    G, sync);
 
     // prepare: cab[idx(b')][idx(a')] += coef * raw[idx(b)][idx(a)]
     const int n1c = ncoset(la_c), n2c = ncoset(lb_c);
-    for (int q = lane; q < n1c * n2c; q += 32)
+    for (int q = lane; q < n1c * n2c; q += G)
       s_cab[q] = 0.0;
-    __syncwarp();
+    __syncwarp(gmask);
     const int a_lo = ncoset(T.la_min - 1), a_hi = ncoset(T.la_max);
     const int b_lo = ncoset(T.lb_min - 1), b_hi = ncoset(T.lb_max);
     const int npa = a_hi - a_lo, npb = b_hi - b_lo;
-    for (int q = lane; q < npa * npb; q += 32) {
+    for (int q = lane; q < npa * npb; q += G) {
       const int ia = a_lo + q % npa, ib = b_lo + q / npa;
       const double p = s_raw[ib * T.ncoseta + ia];
       if (func == 100) {
@@ -302,9 +307,9 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
         }
       }
     }
-    __syncwarp();
+    __syncwarp(gmask);
 
-    make_alpha(T, la_c, lb_c, s_alpha, lane, 32, sync);
+    make_alpha(T, la_c, lb_c, s_alpha, lane, G, sync);
 
     // gather: cxyz[k] = prefactor * sum_{a,b} cab[b][a] ax ay az
     const double rscale = (T.iatom == T.jatom) ? 1.0 : 2.0;
@@ -316,7 +321,7 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
     const int cchunk = max(1, D.part / nbr);  // coefficients per pass (scratch size)
     for (int c0 = 0; c0 < nc; c0 += cchunk) {
     const int ncc = min(cchunk, nc - c0);
-    for (int q = lane; q < ncc * nbr; q += 32) {
+    for (int q = lane; q < ncc * nbr; q += G) {
       const int c = c0 + q / nbr, ib = cb_lo + q % nbr;
       const Orb k = orb_of(s_orb, c), b = orb_of(s_orb, ib);
       double acc = 0.0;
@@ -334,8 +339,8 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
       }
       s_part[q] = acc;
     }
-    __syncwarp();
-    for (int cc = lane; cc < ncc; cc += 32) {
+    __syncwarp(gmask);
+    for (int cc = lane; cc < ncc; cc += G) {
       double acc = 0.0;
       for (int j = 0; j < nbr; j++)
         acc += s_part[cc * nbr + j];
@@ -344,19 +349,19 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
       else
         out[c0 + cc] = acc;
     }
-    __syncwarp();
+    __syncwarp(gmask);
     }
     if (to_cijk) {  // lattice-polynomial basis for the general path
-      __syncwarp();
+      __syncwarp(gmask);
       const double *Tm = L.cijk_T[T.level * (kMaxLp + 1) + lp];
-      for (int q = lane; q < nc; q += 32) {
+      for (int q = lane; q < nc; q += G) {
         double acc = 0.0;
         for (int c = 0; c < nc; c++)
           acc += __ldg(&Tm[q * nc + c]) * s_cxyz[c];
         out[q] = acc;
       }
     }
-    __syncwarp();
+    __syncwarp(gmask);
   }
 }
 
@@ -418,6 +423,7 @@ struct HabDims {
 // One warp per task (tasks visited in block order for locality).  The spherical
 // block receives the task's contribution through FP64 atomics: tasks of one
 // block are few (~8 for water) and the atomics are spread over the whole block.
+template <int G>
 __global__ void __launch_bounds__(128)
 coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const int dla_max,
                    const int dla_min, const int dlb_max, const int dlb_min) {
@@ -425,7 +431,8 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
   __shared__ unsigned s_orb[kOrbEntries];
   stage_orb_table(s_orb, threadIdx.x, blockDim.x);
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int lane = threadIdx.x & (G - 1), warp = threadIdx.x / G, wpc = blockDim.x / G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
   double *s_work = smem + (size_t)warp * D.total();
   double *s_raw = s_work + D.work;
   double *s_cab = s_raw + D.raw;
@@ -433,7 +440,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
   double *s_cxyz = s_alpha + D.alpha;
   double *s_cijk = s_cxyz + D.cxyz;
   double *s_h = s_cijk + D.cxyz;
-  auto sync = [] { __syncwarp(); };
+  auto sync = [gmask] { __syncwarp(gmask); };
   const bool do_f = (L.forces != nullptr), do_v = (L.virial != nullptr);
 
   for (int it = blockIdx.x * wpc + warp; it < ntasks; it += gridDim.x * wpc) {
@@ -449,26 +456,26 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
 
     // (1) coefficients, back to the Cartesian polynomial basis if needed
     if (T.use_ortho) {
-      for (int c = lane; c < nc; c += 32)
+      for (int c = lane; c < nc; c += G)
         s_cxyz[c] = in[c];
     } else {
-      for (int c = lane; c < nc; c += 32)
+      for (int c = lane; c < nc; c += G)
         s_cijk[c] = in[c];
-      __syncwarp();
+      __syncwarp(gmask);
       const double *Tm = L.cijk_T[T.level * (kMaxLp + 1) + lp];
-      for (int c = lane; c < nc; c += 32) {
+      for (int c = lane; c < nc; c += G) {
         double acc = 0.0;
         for (int q = 0; q < nc; q++)
           acc += __ldg(&Tm[q * nc + c]) * s_cijk[q];
         s_cxyz[c] = acc;
       }
     }
-    make_alpha(T, la_c, lb_c, s_alpha, lane, 32, sync);  // syncs
+    make_alpha(T, la_c, lb_c, s_alpha, lane, G, sync);  // syncs
 
     // (2) cab[b][a] = prefactor * sum_k cxyz[k] ax ay az
     const int n1c = ncoset(la_c), n2c = ncoset(lb_c);
     const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
-    for (int q = lane; q < n1c * n2c; q += 32) {
+    for (int q = lane; q < n1c * n2c; q += G) {
       const int ia = q % n1c, ib = q / n1c;
       double acc = 0.0;
       if (ia >= ca_lo && ib >= cb_lo) {
@@ -485,8 +492,8 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
     }
     // (3) density sub-block for forces / virial
     if (do_f || do_v)
-      decontract_task(T, L.pab + T.block_offset, L.sphi_pool, s_work, s_raw, lane, 32, sync);
-    __syncwarp();
+      decontract_task(T, L.pab + T.block_offset, L.sphi_pool, s_work, s_raw, lane, G, sync);
+    __syncwarp(gmask);
 
     // (4) matrix elements for the original l-range
     PCtx P;
@@ -498,7 +505,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
 #pragma unroll
     for (int i = 0; i < 15; i++)
       facc[i] = 0.0;
-    for (int q = lane; q < na * nb; q += 32) {
+    for (int q = lane; q < na * nb; q += G) {
       const int ia = q % na, ib = q / na;
       double hval = 0.0;
       if (ia >= a_lo && ib >= b_lo) {
@@ -506,12 +513,15 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
         hval = vab_elem(P, L.compute_tau, 0, 0, 0, a, b);
         if (do_f) {
           const double pv = s_raw[ib * na + ia];
+#pragma unroll
           for (int i = 0; i < 3; i++) {
             facc[i] += pv * vab_elem(P, L.compute_tau, 1, i, 0, a, b);
             facc[3 + i] += pv * vab_elem(P, L.compute_tau, 2, i, 0, a, b);
           }
           if (do_v)
+#pragma unroll
             for (int i = 0; i < 3; i++)
+#pragma unroll
               for (int j = 0; j < 3; j++)
                 facc[6 + 3 * i + j] +=
                     pv * (vab_elem(P, L.compute_tau, 3, i, j, a, b) +
@@ -520,21 +530,21 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
       }
       s_h[q] = hval;
     }
-    __syncwarp();
+    __syncwarp(gmask);
 
     // (5) contract into the spherical block: block += sphi_a h sphi_b^T
     const double *sphi_a = L.sphi_pool + T.sphi_a + T.sgfa * T.maxcoa + T.o1;
     const double *sphi_b = L.sphi_pool + T.sphi_b + T.sgfb * T.maxcob + T.o2;
-    for (int q = lane; q < T.nsgf_setb * na; q += 32) {
+    for (int q = lane; q < T.nsgf_setb * na; q += G) {
       const int sb = q / na, ico = q % na;
       double acc = 0.0;
       for (int jco = 0; jco < nb; jco++)
         acc += __ldg(&sphi_b[sb * T.maxcob + jco]) * s_h[jco * na + ico];
       s_work[q] = acc;
     }
-    __syncwarp();
+    __syncwarp(gmask);
     double *g_block = L.hab + T.block_offset;
-    for (int q = lane; q < T.nsgf_seta * T.nsgf_setb; q += 32) {
+    for (int q = lane; q < T.nsgf_seta * T.nsgf_setb; q += G) {
       const int sa = q % T.nsgf_seta, sb = q / T.nsgf_seta;
       double acc = 0.0;
       for (int ico = 0; ico < na; ico++)
@@ -547,10 +557,14 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
     if (do_f) {
       const int nred = do_v ? 15 : 6;
       const double scale = (T.iatom == T.jatom) ? 1.0 : 2.0;
-      for (int i = 0; i < nred; i++) {
+#pragma unroll
+      for (int i = 0; i < 15; i++) {
+        if (i >= nred)
+          break;
         double v = facc[i];
-        for (int o = 16; o > 0; o >>= 1)
-          v += __shfl_xor_sync(0xffffffffu, v, o);
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1)
+          v += __shfl_xor_sync(gmask, v, o);
         if (lane == 0 && v != 0.0) {
           if (i < 3)
             atomicAdd(&L.forces[3 * T.iatom + i], scale * v);
@@ -561,7 +575,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
         }
       }
     }
-    __syncwarp();
+    __syncwarp(gmask);
   }
 }
 
@@ -582,14 +596,22 @@ inline void launch_pab_to_coef(const CoefLaunch &L, const int func, const double
   D.alpha = 3 * (max_la_c + 1) * (max_lb_c + 1) * (max_la_c + max_lb_c + 1);
   D.cxyz = ncoset(max_la_c + max_lb_c);
   D.part = std::min(ncoset(max_la_c + max_lb_c) * ncoset(max_lb_c), std::max(1024, ncoset(max_lb_c)));
-  const size_t per_warp = (size_t)D.total() * sizeof(double);
-  B200_ASSERT(per_warp <= kSmemBudget, "basis too large for the coefficient kernel");
-  const int wpc = (int)std::min<size_t>(4, kSmemBudget / per_warp);
-  const size_t bytes = per_warp * wpc;
-  B200_CHECK(cudaFuncSetAttribute(pab_to_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)bytes));
-  const int grid = std::min((L.ntasks + wpc - 1) / wpc, 148 * 16);
-  pab_to_coef_kernel<<<grid, 32 * wpc, bytes, L.stream>>>(L, func, pab, D);
+  const size_t per_group = (size_t)D.total() * sizeof(double);
+  B200_ASSERT(per_group <= kSmemBudget, "basis too large for the coefficient kernel");
+  // half-warp groups when two of them fit (small tasks), else one warp per task
+  const int gpw = (8 * per_group <= kSmemBudget) ? 2 : 1;
+  const int wpc = (int)std::min<size_t>(4, kSmemBudget / (per_group * gpw));
+  const size_t bytes = per_group * gpw * wpc;
+  const int grid = std::min((L.ntasks + gpw * wpc - 1) / (gpw * wpc), 148 * 16);
+  if (gpw == 2) {
+    B200_CHECK(cudaFuncSetAttribute(pab_to_coef_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)bytes));
+    pab_to_coef_kernel<16><<<grid, 32 * wpc, bytes, L.stream>>>(L, func, pab, D);
+  } else {
+    B200_CHECK(cudaFuncSetAttribute(pab_to_coef_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)bytes));
+    pab_to_coef_kernel<32><<<grid, 32 * wpc, bytes, L.stream>>>(L, func, pab, D);
+  }
   B200_CHECK(cudaGetLastError());
   count_launch();
 }
@@ -606,15 +628,23 @@ inline void launch_coef_to_hab(const HabLaunch &L, const int ntasks, const int m
   D.alpha = 3 * (L.max_la_l + 1) * (L.max_lb_l + 1) * (L.max_la_l + L.max_lb_l + 1);
   D.cxyz = ncoset(L.max_la_l + L.max_lb_l);
   D.h = max_ncoset_raw * max_ncoset_raw;
-  const size_t per_warp = (size_t)D.total() * sizeof(double);
-  B200_ASSERT(per_warp <= kSmemBudget, "basis too large for the hab kernel");
-  const int wpc = (int)std::min<size_t>(4, kSmemBudget / per_warp);
-  const size_t bytes = per_warp * wpc;
-  B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)bytes));
-  const int grid = std::min((ntasks + wpc - 1) / wpc, 148 * 16);
-  coef_to_hab_kernel<<<grid, 32 * wpc, bytes, L.stream>>>(L, D, ntasks, dla_max, dla_min, dlb_max,
-                                                         dlb_min);
+  const size_t per_group = (size_t)D.total() * sizeof(double);
+  B200_ASSERT(per_group <= kSmemBudget, "basis too large for the hab kernel");
+  const int gpw = (8 * per_group <= kSmemBudget) ? 2 : 1;
+  const int wpc = (int)std::min<size_t>(4, kSmemBudget / (per_group * gpw));
+  const size_t bytes = per_group * gpw * wpc;
+  const int grid = std::min((ntasks + gpw * wpc - 1) / (gpw * wpc), 148 * 16);
+  if (gpw == 2) {
+    B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)bytes));
+    coef_to_hab_kernel<16><<<grid, 32 * wpc, bytes, L.stream>>>(L, D, ntasks, dla_max, dla_min, dlb_max,
+                                                               dlb_min);
+  } else {
+    B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)bytes));
+    coef_to_hab_kernel<32><<<grid, 32 * wpc, bytes, L.stream>>>(L, D, ntasks, dla_max, dla_min, dlb_max,
+                                                               dlb_min);
+  }
   B200_CHECK(cudaGetLastError());
   count_launch();
 }
