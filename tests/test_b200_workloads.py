@@ -1,0 +1,113 @@
+"""GPU parity on realistic task lists (water benchmarks, TZV2P-GTH) and on
+distributed (z-slab) grid layouts, plus size-independent properties at the full
+benchmark size: collocate and integrate are adjoint linear maps,
+    sum_blocks w_b <P_b, H_b(V)>  ==  <rho(P), V>,   w_b = 1 (same atom) or 2,
+(the factor is the reference's rscale, src/grid/ref/grid_ref_task_list.c:369)."""
+import numpy as np
+import pytest
+
+from cp2k_b200.grid_api import GRID_BACKEND_CPU, OffloadBuffer
+from cp2k_b200 import rsgrid
+from cp2k_b200.workload import build_h2o_workload
+from replay import rel_diff
+from synth import make_workload
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(lib, wl, pab, forces=True, func=100, tau=False):
+    tl = wl.create(lib)
+    grids = wl.new_grids()
+    tl.collocate(func, pab, grids)
+    hab = OffloadBuffer(wl.pab_len)
+    f = np.zeros((wl.natoms, 3)) if forces else None
+    v = np.zeros((3, 3)) if forces else None
+    tl.integrate(tau, pab if forces else None, grids, hab, f, v)
+    tl.free()
+    return [g.host.copy() for g in grids], hab.host.copy(), f, v
+
+
+@pytest.fixture(scope="module")
+def h2o_small():
+    return build_h2o_workload("H2O-64", max_atoms=36)
+
+
+def test_h2o_subset_against_reference_cpu_backend(b200, reference, h2o_small):
+    wl = h2o_small
+    assert wl.ntasks > 5000
+    pab = wl.random_pab(11)
+    ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab)
+    got = _run(b200, wl, pab)
+    for a, b in zip(got[0], ref[0]):
+        assert rel_diff(a, b) < 1e-10
+    assert rel_diff(got[1], ref[1]) < 1e-10
+    assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
+
+
+@pytest.mark.parametrize("func,tau", [(200, True), (502, False)])
+def test_h2o_subset_tau_and_gradient(b200, oracle, h2o_small, func, tau):
+    wl = h2o_small.subset(np.arange(0, h2o_small.ntasks, 7))
+    pab = wl.random_pab(12)
+    ref = _run(oracle, wl, pab, forces=False, func=func, tau=tau)
+    got = _run(b200, wl, pab, forces=False, func=func, tau=tau)
+    for a, b in zip(got[0], ref[0]):
+        assert rel_diff(a, b) < 1e-10
+    assert rel_diff(got[1], ref[1]) < 1e-10
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_layouts_every_rank(b200, oracle, world):
+    """npts_local != npts_global with halos: every rank's local task list."""
+    wl = make_workload(seed=51, natoms=6, max_tasks=700, edge=(9.0, 10.0, 18.0),
+                       npts_list=((40, 45, 80), (20, 24, 40)))
+    levels = rsgrid.make_slab_levels(wl, world)
+    assert any(l.distributed for l in levels)
+    pab = wl.random_pab(13)
+    for rank in range(world):
+        mine = rsgrid.local_workload(wl, levels, rank, world)
+        ref = _run(oracle, mine, pab, forces=False)
+        got = _run(b200, mine, pab, forces=False)
+        for a, b in zip(got[0], ref[0]):
+            assert rel_diff(a, b) < 1e-10
+        assert rel_diff(got[1], ref[1]) < 1e-10
+
+
+def _adjoint_defect(lib, wl, seed):
+    tl = wl.create(lib)
+    pab = wl.random_pab(seed)
+    rho = wl.new_grids()
+    tl.collocate(100, pab, rho)
+    rng = np.random.default_rng(seed + 1)
+    pot = wl.new_grids()
+    for g in pot:
+        g.host[:] = rng.normal(size=g.host.size)
+    hab = OffloadBuffer(wl.pab_len)
+    tl.integrate(False, None, pot, hab)
+    # block weights: a block (atom pair) is diagonal iff its tasks have iatom == jatom
+    diag = np.zeros(wl.nblocks, dtype=bool)
+    t = wl.tasks
+    diag[t["block_num_list"][t["iatom_list"] == t["jatom_list"]] - 1] = True
+    sizes = np.diff(np.append(wl.block_offsets, wl.pab_len))
+    w = np.repeat(np.where(diag, 1.0, 2.0), sizes)
+    lhs = float(np.sum(w * pab.host * hab.host))
+    rhs = float(sum(np.dot(r.host, p.host) for r, p in zip(rho, pot)))
+    # linearity on the way: collocate(2 P) == 2 collocate(P)
+    pab2 = OffloadBuffer(wl.pab_len)
+    pab2.host[:] = 2.0 * pab.host
+    rho2 = wl.new_grids()
+    tl.collocate(100, pab2, rho2)
+    lin = max(rel_diff(a.host, 2.0 * b.host) for a, b in zip(rho2, rho))
+    tl.free()
+    scale = float(np.sqrt(sum(np.dot(r.host, r.host) for r in rho) * sum(np.dot(p.host, p.host) for p in pot)))
+    return abs(lhs - rhs) / scale, lin
+
+
+def test_adjointness_h2o64_full(b200):
+    defect, lin = _adjoint_defect(b200, build_h2o_workload("H2O-64"), 21)
+    assert defect < 1e-12 and lin < 1e-12
+
+
+def test_adjointness_h2o256_full_size(b200):
+    """BASELINE.json's headline configuration, all 1.25 M tasks."""
+    defect, lin = _adjoint_defect(b200, build_h2o_workload("H2O-256"), 22)
+    assert defect < 1e-12 and lin < 1e-12
