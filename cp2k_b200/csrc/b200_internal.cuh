@@ -50,10 +50,10 @@ constexpr int kMaxLSide = 8;   // max angular momentum per side after ldiffs
 constexpr int kMaxLp = 16;     // max la+lb after ldiffs
 constexpr int kNumOrb = 165;   // ncoset(kMaxLSide)
 
-__host__ __device__ inline int ncoset(const int l) {
+__host__ __device__ constexpr int ncoset(const int l) {
   return (l < 0) ? 0 : ((l + 1) * (l + 2) * (l + 3)) / 6;
 }
-__host__ __device__ inline int coset(const int lx, const int ly, const int lz) {
+__host__ __device__ constexpr int coset(const int lx, const int ly, const int lz) {
   const int l = lx + ly + lz;
   return ncoset(l - 1) + ((l - lx) * (l - lx + 1)) / 2 + lz;
 }

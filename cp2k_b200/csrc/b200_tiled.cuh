@@ -12,19 +12,27 @@
 // exactly once (a RED flush for collocate, one load for integrate).
 //
 //   * pairs are generated once per task list ON THE GPU (count / scan / fill),
-//     bucketed by (block, lp); periodic images become separate pairs;
+//     bucketed by (block, lp); periodic images become separate pairs; a pair
+//     exists only if the task's sphere really meets the block, and carries the
+//     warp-uniform part of the per-pair work precomputed (sphere-table index,
+//     plane range);
 //   * the separable Gaussian factors exp(-zetp (x-xp)^2) of every task are
 //     tabulated once per task list (they depend on geometry only) -- there is
 //     no exp() in the hot loop; a (pair, warp) step loads exactly one table
 //     entry per lane (8 x-, 8 y-, 16 z-entries);
-//   * which points of a cube are inside the (discretised-radius) sphere is a
-//     table lookup: because the reference discretises the radius to n*drmin
-//     (ref/grid_ref_collint.h:237-239) the admissible z-extent of a column
-//     depends only on (n, |j|, |i|); the table is built on the host with the
-//     reference's own expressions, so the SET of touched points is identical;
+//   * which points of a cube are inside the (discretised-radius) sphere is two
+//     table lookups per column: because the reference discretises the radius to
+//     n*drmin (ref/grid_ref_collint.h:237-239) the admissible z-extent K of a
+//     column depends only on (n, |j|, |i|); the table is built on the host with
+//     the reference's own expressions, so the SET of touched points is
+//     identical.  A second table turns (K, centre plane) into a 16-bit plane
+//     mask; the masks drive PREDICATED DFMAs (no selects);
 //   * planes no lane of the warp needs are skipped warp-uniformly;
+//   * a work item's pairs are ordered by lp and each lp has its own fully
+//     specialised pair loop (no switch inside the loop);
 //   * the next pair's record, table entry and coefficients are prefetched
-//     while the current pair is processed.
+//     while the current pair is processed; the per-pair scratch in shared
+//     memory is double buffered (one __syncwarp per pair).
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -41,7 +49,13 @@ constexpr int kBX = 8, kBY = 8, kBZ = 16;     // block (warp footprint)
 constexpr int kTiledThreads = 128;            // 4 autonomous warps
 constexpr int kTiledWarps = kTiledThreads / 32;
 constexpr int kTiledMaxLp = 6;                // beyond: generic kernels
-constexpr int kTiledMaxN = 30;                // max discretised radius index (sphere tables <= ~40 KB)
+constexpr int kTiledMaxNb = 23;               // max cube half-width (sphere-table rows are 64 bytes)
+constexpr int kTiledMaxN = 30;                // max discretised radius index
+constexpr int kKPitch = 64;                   // sphere-table row pitch (bytes)
+constexpr int kKPad = 8;                      // margin around the cube: block offsets need no bounds check
+constexpr int kZmPitch = 64;                  // plane-mask table: [K+1][oz + kZmBias]
+constexpr int kZmBias = 24;
+constexpr int kZmRows = kTiledMaxNb + 2;
 constexpr int kLpBuckets = kTiledMaxLp + 1;
 constexpr int kItemPairs = 512;               // pairs per work item (upper bound)
 // lp classes (by lp0 = la_max + lb_max): separate kernel instantiations keep the
@@ -60,22 +74,21 @@ struct TTask {            // static per-task data of the tiled path
   int task;               // index into the TaskDev array
 };
 
-struct TPair {            // 8 bytes
-  unsigned key;           // ttask (21 bits) | n << 21 (6 bits) | lp0 << 27 (3 bits)
-  signed char o[3];       // cube centre relative to the block origin
-  unsigned char pad;
+struct alignas(16) TPair {  // 16 bytes, read as one uint4 (warp-uniform)
+  unsigned q;             // ttask index
+  unsigned kbase;         // sphere-table index of block column (0,0)
+  unsigned opk;           // byte 0..2: cube centre relative to the block origin (signed), byte 3: wlo | whi << 4
+  unsigned pad;
 };
-__host__ __device__ inline int pair_ttask(const TPair &P) { return (int)(P.key & 0x1fffffu); }
-__host__ __device__ inline int pair_n(const TPair &P) { return (int)((P.key >> 21) & 63u); }
-__host__ __device__ inline int pair_lp0(const TPair &P) { return (int)(P.key >> 27); }
 
-struct TWork {
+struct alignas(16) TWork {  // 32 bytes
   int x0, y0, z0;         // block origin (local grid indices)
-  int first, last;        // pair range
+  int b[4];               // pair ranges per lp of the class: [b[i], b[i+1])
+  int pad;
 };
 
-struct alignas(16) KTabHeader {  // per radius index n (read as one int4 on the device)
-  int offset;             // into the byte table
+struct alignas(16) KTabHeader {  // per radius index n
+  int offset;             // into the byte table, -1: not tabulated
   int nbx, nby, nbz;      // -lb per axis
 };
 
@@ -91,7 +104,6 @@ struct TiledLevel {
   int *d_class_task_ids[kNumClasses] = {nullptr, nullptr, nullptr};  // TaskDev ids per class
   int ntasks_tiled = 0;
   int max_lp0 = 0;
-  int ktab_bytes = 0;
   int max_n = 0;
   int P = 0;              // exp-table pitch per axis: entries g = -P/2+1 .. P/2
   TTask *d_ttasks = nullptr;
@@ -99,40 +111,40 @@ struct TiledLevel {
   TWork *d_work = nullptr;
   int *d_counters = nullptr;         // one per (direction, class)
   KTabHeader *d_khead = nullptr;
-  signed char *d_ktab = nullptr;
+  unsigned char *d_ktab = nullptr;   // K+1 per (n, dj, di), 0 outside the sphere
+  unsigned short *d_zmask = nullptr; // [kZmRows][kZmPitch]
   double *d_etab = nullptr;          // [ttask][3][P]
-  int *d_tcoef[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void release() {
     cudaFree(d_ttasks), cudaFree(d_pairs), cudaFree(d_work), cudaFree(d_khead), cudaFree(d_ktab);
-    cudaFree(d_etab);
+    cudaFree(d_etab), cudaFree(d_zmask);
     cudaFree(d_counters);
     d_counters = nullptr;
     for (auto &p : d_class_task_ids) {
       cudaFree(p);
       p = nullptr;
     }
-    for (auto &p : d_tcoef) {
-      cudaFree(p);
-      p = nullptr;
-    }
     d_ttasks = nullptr, d_pairs = nullptr, d_work = nullptr, d_khead = nullptr, d_ktab = nullptr;
-    d_etab = nullptr;
+    d_etab = nullptr, d_zmask = nullptr;
     npairs = 0, nwork = 0, ntasks_tiled = 0;
   }
 };
 
 // ---------------------------------------------------------------------------
-// Host: sphere-extent tables.  K[n][mj][mi] = largest z pair-distance kd such
-// that the point (kd, mj, mi) is visited by the reference's loop nest
-// (ref/grid_ref_collint.h:144-147, 46-50, 237-254), or -1.
+// Host: sphere-extent tables.  For the discretised radius n*drmin the largest
+// z pair-distance K such that the point (K, mj, mi) is visited by the
+// reference's loop nest (ref/grid_ref_collint.h:144-147, 46-50, 237-254).
+// Stored as K+1 (0 = column outside the sphere) by SIGNED cube offsets with a
+// margin of kKPad on every side and a fixed row pitch:
+//   tab[offset_n + (dj + nby + kKPad) * kKPitch + (di + nbx + kKPad)]
+// so that a block column (li, lj) of a pair reads tab[kbase + lj*kKPitch + li]
+// with kbase = offset_n + (nby + kKPad - oy) * kKPitch + (nbx + kKPad - ox).
 // ---------------------------------------------------------------------------
 inline void build_ktabs(const LevelDev &L, const int max_n, std::vector<KTabHeader> &heads,
-                        std::vector<signed char> &tab) {
-  // Stored by SIGNED cube offsets: K[n][dj + nby][di + nbx], dj in [-nby, nby+1].
+                        std::vector<unsigned char> &tab) {
   const double h[3] = {L.dh[0], L.dh[4], L.dh[8]};
   const double hinv[3] = {L.dh_inv[0], L.dh_inv[4], L.dh_inv[8]};
   const double drmin = fmin(h[0], fmin(h[1], h[2]));
-  heads.assign(max_n + 1, KTabHeader{0, 0, 0, 0});
+  heads.assign(max_n + 1, KTabHeader{-1, 0, 0, 0});
   tab.clear();
   for (int n = 1; n <= max_n; n++) {
     const double R = drmin * fmax(1.0, (double)n);
@@ -140,10 +152,12 @@ inline void build_ktabs(const LevelDev &L, const int max_n, std::vector<KTabHead
     for (int d = 0; d < 3; d++)
       nb[d] = -(int)ceil(-1e-8 - R * hinv[d]);
     KTabHeader H;
-    H.offset = (int)tab.size();
-    H.nbx = nb[0], H.nby = nb[1], H.nbz = nb[2];
+    H.offset = -1, H.nbx = nb[0], H.nby = nb[1], H.nbz = nb[2];
+    heads[n] = H;
+    if (nb[0] > kTiledMaxNb || nb[1] > kTiledMaxNb || nb[2] > kTiledMaxNb)
+      continue;
     const int px = nb[0] + 1, py = nb[1] + 1;
-    std::vector<signed char> K((size_t)px * py, (signed char)-1);
+    std::vector<int> K((size_t)px * py, -1);
     for (int kd = 0; kd <= nb[2]; kd++) {
       const double kr = kd * h[2];
       const double krem = R * R - kr * kr;
@@ -153,18 +167,37 @@ inline void build_ktabs(const LevelDev &L, const int max_n, std::vector<KTabHead
         const double jrem = krem - jr * jr;
         const int istart = (int)ceil(-1e-8 - sqrt(fmax(0.0, jrem)) * hinv[0]);
         for (int id = 0; id <= -istart && id <= nb[0]; id++)
-          K[(size_t)jd * px + id] = (signed char)std::max<int>(K[(size_t)jd * px + id], kd);
+          K[(size_t)jd * px + id] = std::max<int>(K[(size_t)jd * px + id], kd);
       }
     }
-    const int wx = 2 * nb[0] + 2, wy = 2 * nb[1] + 2;
-    for (int tj = 0; tj < wy; tj++)
-      for (int ti = 0; ti < wx; ti++) {
-        const int dj = tj - nb[1], di = ti - nb[0];
+    H.offset = (int)tab.size();
+    const int rows = 2 * nb[1] + 2 * kKPad + 1;
+    tab.resize(tab.size() + (size_t)rows * kKPitch, (unsigned char)0);
+    for (int dj = -nb[1]; dj <= nb[1] + 1; dj++)
+      for (int di = -nb[0]; di <= nb[0] + 1; di++) {
         const int mj = (dj <= 0) ? -dj : dj - 1, mi = (di <= 0) ? -di : di - 1;
-        tab.push_back(K[(size_t)mj * px + mi]);
+        tab[(size_t)H.offset + (size_t)(dj + nb[1] + kKPad) * kKPitch + (di + nb[0] + kKPad)] =
+            (unsigned char)(K[(size_t)mj * px + mi] + 1);
       }
     heads[n] = H;
   }
+  tab.resize((tab.size() + 15) / 16 * 16 + 16 * kKPitch, (unsigned char)0);  // slack for the +4 rows of column 1
+}
+
+// zmask[K1][oz + kZmBias]: bit p set <=> plane p of the block lies within
+// pair-distance K = K1 - 1 of the cube centre plane oz:  oz - K <= p <= oz + K + 1
+inline std::vector<unsigned short> build_zmask() {
+  std::vector<unsigned short> zm((size_t)kZmRows * kZmPitch, 0);
+  for (int k1 = 1; k1 < kZmRows; k1++)
+    for (int ozb = 0; ozb < kZmPitch; ozb++) {
+      const int K = k1 - 1, oz = ozb - kZmBias;
+      unsigned m = 0;
+      for (int p = 0; p < kBZ; p++)
+        if (oz - K <= p && p <= oz + K + 1)
+          m |= 1u << p;
+      zm[(size_t)k1 * kZmPitch + ozb] = (unsigned short)m;
+    }
+  return zm;
 }
 
 // ---------------------------------------------------------------------------
@@ -177,7 +210,8 @@ struct PairGenArgs {
   int nx, ny, nz, Nx, Ny, Nz;     // local / global grid size
   int nbx, nby, nbz;              // number of blocks per axis
   unsigned nblocks;
-  double hx, hy, hz, drmin;
+  const KTabHeader *khead;
+  const unsigned char *ktab;
   unsigned int *bucket_count;     // pass 0
   const unsigned int *bucket_start;  // pass 1
   unsigned int *bucket_cursor;    // pass 1
@@ -187,7 +221,7 @@ struct PairGenArgs {
 __device__ inline int floor_div(const int a, const int b) {  // b > 0
   return (a >= 0) ? a / b : -((-a + b - 1) / b);
 }
-__device__ inline int rel_dmin(const int a, const int b) {  // min pair distance over [a,b]
+__device__ inline int rel_dmin(const int a, const int b) {  // min pair distance over cube offsets [a,b]
   return (a <= 1 && b >= 0) ? 0 : ((a > 1) ? a - 1 : -b);
 }
 
@@ -196,11 +230,9 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
   if (q >= A.nttasks)
     return;
   const TTask X = A.ttasks[q];
-  const double R = A.drmin * (double)X.n;
-  const double R2 = R * R * (1.0 + 1e-9) + 1e-12;
+  const KTabHeader H = A.khead[X.n];
   const int nloc[3] = {A.nx, A.ny, A.nz}, N[3] = {A.Nx, A.Ny, A.Nz};
   const int B[3] = {kBX, kBY, kBZ}, nblk[3] = {A.nbx, A.nby, A.nbz};
-  const double h[3] = {A.hx, A.hy, A.hz};
   // per axis: image range
   int m_lo[3], m_hi[3];
   for (int d = 0; d < 3; d++) {
@@ -210,6 +242,7 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
     m_lo[d] = floor_div(-hi, N[d]);
     m_hi[d] = floor_div(nloc[d] - 1 - lo, N[d]) + 1;
   }
+  const unsigned char *ktab_n = A.ktab + H.offset;
   for (int mz = m_lo[2]; mz <= m_hi[2]; mz++) {
     const int cz = X.cc[2] + mz * N[2];
     const int az = max(cz - X.nb[2], 0), bz = min(cz + 1 + X.nb[2], nloc[2] - 1);
@@ -217,7 +250,8 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
       continue;
     for (int tz = az / B[2]; tz <= bz / B[2] && tz < nblk[2]; tz++) {
       const int oz = cz - tz * B[2];
-      const double dz = rel_dmin(max(az, tz * B[2]) - cz, min(bz, tz * B[2] + B[2] - 1) - cz) * h[2];
+      const int zlo = max(az, tz * B[2]) - tz * B[2], zhi = min(bz, tz * B[2] + B[2] - 1) - tz * B[2];
+      const int mk = rel_dmin(zlo - oz, zhi - oz);
       for (int my = m_lo[1]; my <= m_hi[1]; my++) {
         const int cy = X.cc[1] + my * N[1];
         const int ay = max(cy - X.nb[1], 0), by = min(cy + 1 + X.nb[1], nloc[1] - 1);
@@ -225,8 +259,9 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
           continue;
         for (int ty = ay / B[1]; ty <= by / B[1] && ty < nblk[1]; ty++) {
           const int oy = cy - ty * B[1];
-          const double dy = rel_dmin(max(ay, ty * B[1]) - cy, min(by, ty * B[1] + B[1] - 1) - cy) * h[1];
-          if (dz * dz + dy * dy > R2)
+          const int mj = rel_dmin(max(ay, ty * B[1]) - cy, min(by, ty * B[1] + B[1] - 1) - cy);
+          // the widest column of this row of blocks (mi = 0) must reach the block's planes
+          if ((int)ktab_n[(X.nb[1] + kKPad - mj) * kKPitch + (X.nb[0] + kKPad)] - 1 < mk)
             continue;
           for (int mx = m_lo[0]; mx <= m_hi[0]; mx++) {
             const int cx = X.cc[0] + mx * N[0];
@@ -235,9 +270,12 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
               continue;
             for (int tx = ax / B[0]; tx <= bx / B[0] && tx < nblk[0]; tx++) {
               const int ox = cx - tx * B[0];
-              const double dx = rel_dmin(max(ax, tx * B[0]) - cx, min(bx, tx * B[0] + B[0] - 1) - cx) * h[0];
-              if (dx * dx + dy * dy + dz * dz > R2)
-                continue;
+              const int mi = rel_dmin(max(ax, tx * B[0]) - cx, min(bx, tx * B[0] + B[0] - 1) - cx);
+              // K of the block's column nearest to the centre bounds every other column's
+              const int K = (int)ktab_n[(X.nb[1] + kKPad - mj) * kKPitch + (X.nb[0] + kKPad - mi)] - 1;
+              const int wlo = max(zlo, oz - K), whi = min(zhi, oz + K + 1);
+              if (K < 0 || wlo > whi)
+                continue;  // the sphere misses this block
               const unsigned blk = (unsigned)((tz * nblk[1] + ty) * nblk[0] + tx);
               const unsigned bucket = ((unsigned)lp_class(X.lp0) * A.nblocks + blk) * kLpBuckets + X.lp0;
               if (PASS == 0) {
@@ -245,8 +283,10 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
               } else {
                 const unsigned pos = A.bucket_start[bucket] + atomicAdd(&A.bucket_cursor[bucket], 1u);
                 TPair P;
-                P.key = (unsigned)q | ((unsigned)X.n << 21) | ((unsigned)X.lp0 << 27);
-                P.o[0] = (signed char)ox, P.o[1] = (signed char)oy, P.o[2] = (signed char)oz;
+                P.q = (unsigned)q;
+                P.kbase = (unsigned)(H.offset + (X.nb[1] + kKPad - oy) * kKPitch + (X.nb[0] + kKPad - ox));
+                P.opk = ((unsigned)ox & 0xffu) | (((unsigned)oy & 0xffu) << 8) | (((unsigned)oz & 0xffu) << 16) |
+                        ((unsigned)wlo << 24) | ((unsigned)whi << 28);
                 P.pad = 0;
                 A.pairs[pos] = P;
               }
@@ -285,12 +325,6 @@ __global__ void etab_kernel(const TTask *ttasks, const TaskDev *tasks, const int
   etab[idx] = v;
 }
 
-__global__ void tcoef_kernel(const TTask *ttasks, const int nttasks, const int *coef_offsets, int *tcoef) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < nttasks)
-    tcoef[q] = coef_offsets[ttasks[q].task];
-}
-
 // ---------------------------------------------------------------------------
 // Host: per-level build.
 // ---------------------------------------------------------------------------
@@ -316,7 +350,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
       ok = (n >= 1 && n <= kTiledMaxN && T.disr_radius == drmin * fmax(1.0, (double)n));
       ok = ok && (T.la_max + T.lb_max <= kTiledMaxLp);
       for (int d = 0; d < 3; d++)
-        ok = ok && (-T.lb_cube[d] <= 100);
+        ok = ok && (-T.lb_cube[d] <= kTiledMaxNb);
     }
     if (!ok) {
       generic_ids.push_back(it);
@@ -353,15 +387,14 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   for (int c = 0; c < kNumClasses; c++)
     tl.class_tt_first[c + 1] += tl.class_tt_first[c];
   B200_ASSERT(nblocks * kLpBuckets * kNumClasses < (size_t)1 << 31, "too many grid blocks");
-  B200_ASSERT(tt.size() < ((size_t)1 << 21), "too many tasks on one level for the packed pair key");
 
   std::vector<KTabHeader> heads;
-  std::vector<signed char> ktab;
+  std::vector<unsigned char> ktab;
   build_ktabs(L, max_n, heads, ktab);
   for (const TTask &X : tt)  // the cube bounds stored with the task must agree with the table's
-    B200_ASSERT(X.nb[0] == heads[X.n].nbx && X.nb[1] == heads[X.n].nby && X.nb[2] == heads[X.n].nbz,
+    B200_ASSERT(heads[X.n].offset >= 0 && X.nb[0] == heads[X.n].nbx && X.nb[1] == heads[X.n].nby &&
+                    X.nb[2] == heads[X.n].nbz,
                 "cube bounds disagree with the sphere table");
-  tl.ktab_bytes = (int)ktab.size();
   tl.P = 2 * max_nb + 5;  // roff + e(-max_nb-1 .. max_nb+2)
 
   auto up = [&](auto **dst, const auto &vec) {
@@ -372,13 +405,13 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   };
   up(&tl.d_ttasks, tt);
   up(&tl.d_khead, heads);
-  ktab.resize((ktab.size() + 15) / 16 * 16, (signed char)-1);  // copied as 16-byte words
   up(&tl.d_ktab, ktab);
+  const std::vector<unsigned short> zmask = build_zmask();
+  up(&tl.d_zmask, zmask);
 
   // exp tables
   const size_t etab_len = (size_t)tt.size() * 3 * tl.P;
   B200_CHECK(cudaMalloc((void **)&tl.d_etab, etab_len * sizeof(double)));
-  B200_ASSERT(etab_len < ((size_t)1 << 31), "exp tables exceed 2^31 entries on one level");
   etab_kernel<<<(unsigned)((etab_len + 255) / 256), 256, 0, s>>>(tl.d_ttasks, d_tasks, (int)tt.size(), tl.P,
                                                                 max_nb, h[0], h[1], h[2], tl.d_etab);
   B200_CHECK(cudaGetLastError());
@@ -395,7 +428,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   PA.nx = L.npts_local[0], PA.ny = L.npts_local[1], PA.nz = L.npts_local[2];
   PA.Nx = L.npts_global[0], PA.Ny = L.npts_global[1], PA.Nz = L.npts_global[2];
   PA.nbx = nbx, PA.nby = nby, PA.nbz = nbz, PA.nblocks = (unsigned)nblocks;
-  PA.hx = h[0], PA.hy = h[1], PA.hz = h[2], PA.drmin = drmin;
+  PA.khead = tl.d_khead, PA.ktab = tl.d_ktab;
   PA.bucket_count = d_count, PA.bucket_start = d_start, PA.bucket_cursor = nullptr, PA.pairs = nullptr;
   const int pg_blocks = ((int)tt.size() + 127) / 128;
   pairgen_kernel<0><<<pg_blocks, 128, 0, s>>>(PA);
@@ -410,6 +443,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
                              cudaMemcpyDeviceToHost, s));
   B200_CHECK(cudaStreamSynchronize(s));
   const size_t npairs = start[nbuckets];
+  B200_ASSERT(npairs < ((size_t)1 << 31), "too many (task, block) pairs on one level");
   tl.npairs = (long long)npairs;
   B200_CHECK(cudaMalloc((void **)&tl.d_pairs, std::max<size_t>(npairs, 1) * sizeof(TPair)));
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
@@ -418,32 +452,34 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   B200_CHECK(cudaGetLastError());
   count_launch(4);
 
-  // work items per lp class: a block's pairs of that class (contiguous) cut into chunks
+  // work items per lp class: a block's pairs of that class (contiguous, ordered by lp) cut into chunks
   std::vector<TWork> work;
   const size_t target_items = (size_t)148 * 64;
   const int chunk = (int)std::min<size_t>(kItemPairs, std::max<size_t>(128, npairs / target_items + 1));
   for (int cls = 0; cls < kNumClasses; cls++) {
     tl.class_work_first[cls] = (int)work.size();
-    const size_t w0 = work.size();
     for (size_t b = 0; b < nblocks; b++) {
-      const size_t bb = (size_t)cls * nblocks + b;
-      const unsigned f = start[bb * kLpBuckets], e = start[(bb + 1) * kLpBuckets];
+      const size_t bb = ((size_t)cls * nblocks + b) * kLpBuckets;
+      const unsigned f = start[bb], e = start[bb + kLpBuckets];
       if (e == f)
         continue;
       const int bx = (int)(b % nbx), by = (int)((b / nbx) % nby), bz = (int)(b / ((size_t)nbx * nby));
       const int cnt = (int)(e - f), nchunks = (cnt + chunk - 1) / chunk, per = (cnt + nchunks - 1) / nchunks;
       for (int c = 0; c < nchunks; c++) {
         TWork W;
-        W.x0 = bx * kBX, W.y0 = by * kBY, W.z0 = bz * kBZ;
-        W.first = (int)f + c * per;
-        W.last = (int)f + std::min((c + 1) * per, cnt);
+        W.x0 = bx * kBX, W.y0 = by * kBY, W.z0 = bz * kBZ, W.pad = 0;
+        const int lo = (int)f + c * per, hi = (int)f + std::min((c + 1) * per, cnt);
+        W.b[0] = lo, W.b[3] = hi;
+        for (int i = 1; i < 3; i++) {  // end of the class's i-th lp within this chunk
+          const int lp_next = std::min(kClassLo[cls] + i, kLpBuckets);
+          W.b[i] = std::min(std::max((int)start[bb + lp_next], lo), hi);
+        }
         work.push_back(W);
       }
     }
     // Items stay in spatial (block) order: warps that run concurrently then work on
     // neighbouring blocks and share the tasks' table rows through L2.  They are
     // handed out dynamically (atomic counter), so no size sorting is needed.
-    (void)w0;
   }
   tl.class_work_first[kNumClasses] = (int)work.size();
   // TaskDev ids per class (for calls whose l growth pushes a class out of the tiled range)
@@ -475,9 +511,8 @@ struct TiledArgs {
   const TWork *work;         // work items of ONE lp class
   int nwork;
   int *counter;              // dynamic work distribution (zeroed before the launch)
-  const KTabHeader *khead;
-  const signed char *ktab;
-  int ktab_bytes, max_n;
+  const unsigned char *ktab;
+  const unsigned short *zmask;
   const double *etab;        // rows of P doubles per (task, axis)
   int P, max_nb;
   int tt_first;              // first ttask of this class
@@ -486,7 +521,6 @@ struct TiledArgs {
   double *grid;
   int nx, ny, nz;            // npts_local
   double hx, hy, hz;
-  int dl;                    // lp growth of this call
 };
 
 // Transposing warp reduction: on return lane L holds in v[0] the warp-wide sum
@@ -563,9 +597,29 @@ template <int LP> struct IntegrateReduce {
   }
 };
 
-// The 16 planes of a block in pairs (two independent FMA chains per column keep
-// the FP64 pipe fed), entered at the first pair any lane needs and left after the
-// last one (both warp-uniform); planes outside a lane's range are masked.
+// Row pitch (doubles) of the per-pair scratch: even (16-byte rows) except lp = 0.
+__host__ __device__ constexpr int row_pitch(const int lp) { return lp == 0 ? 1 : ((lp + 2) / 2) * 2; }
+__host__ __device__ constexpr int stage_doubles(const int lp) {
+  return 32 * row_pitch(lp) + ((ncoset(lp) + 1) / 2) * 2;
+}
+
+// Loads one scratch row (LP+1 doubles) with 16-byte accesses where possible.
+template <int LP> __device__ __forceinline__ void load_row(const double *__restrict__ row, double (&z)[LP + 1]) {
+  if constexpr (LP == 0) {
+    z[0] = row[0];
+  } else {
+#pragma unroll
+    for (int l = 0; l + 1 <= LP; l += 2) {
+      const double2 v = *reinterpret_cast<const double2 *>(row + l);
+      z[l] = v.x, z[l + 1] = v.y;
+    }
+    if constexpr ((LP & 1) == 0)
+      z[LP] = row[LP];
+  }
+}
+
+// The 16 planes of a block in pairs, entered at the first pair any lane needs
+// and left after the last one (both warp-uniform, precomputed per pair).
 #define B200_PLANES(BODY)                                                      \
   switch (wlo >> 1) {                                                          \
   case 0: BODY(0) BODY(1) if (whi <= 1) break;                                 \
@@ -578,279 +632,274 @@ template <int LP> struct IntegrateReduce {
   default: BODY(14) BODY(15)                                                   \
   }
 
-// One (pair, warp) step.  `ws` is this warp's scratch: [32 entries][LP+1]
-// table rows (0..7 x, 8..15 y, 16..31 z) followed by ncoset(LP) coefficients.
-template <bool COLLOCATE, int LP, int NCL>
-__device__ __forceinline__ void process_pair(double *__restrict__ ws, double *__restrict__ gcoef,
-                                             const double e, const double x, const double (&creg)[NCL],
-                                             const unsigned mask0, const unsigned mask1, const int wlo,
-                                             const int whi, const int li, const int lj, const int lane,
-                                             double (&acc0)[kBZ], double (&acc1)[kBZ]) {
-  constexpr int PITCH = LP + 1;
+// Sign-extended byte at bit position `pos` of `v`.
+__device__ __forceinline__ int sext_byte(const unsigned v, const unsigned pos) {
+  int r;
+  asm("bfe.s32 %0, %1, %2, 8;" : "=r"(r) : "r"(v), "r"(pos));
+  return r;
+}
+
+// Per-lane constants of the pair loops.
+struct LaneCtx {
+  const uint4 *__restrict__ pairs;
+  const double *__restrict__ etab_axis;  // etab + my_axis * P
+  const double *__restrict__ coef_lane;  // coef + coef_base + lane
+  double *__restrict__ coef0;            // coef + coef_base
+  const unsigned char *__restrict__ ktab_lane;  // ktab + lj * kKPitch + li
+  const unsigned short *__restrict__ s_zm;      // shared copy of the plane-mask table (biased)
+  double *__restrict__ ws;               // this warp's scratch (two stages)
+  double my_h;
+  int row3, gbias, ge_max, my_t;
+  unsigned sel;                          // bit position of my axis' byte in opk
+  int tt_first, coef_stride;
+  int lane, li, lj;
+};
+
+// All pairs [first, last) of ONE lp for this warp's block.
+template <bool COLLOCATE, int LP, int STAGE>
+__device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, const int last,
+                                          double (&acc0)[kBZ], double (&acc1)[kBZ]) {
+  if (first >= last)
+    return;
+  constexpr int PITCH = row_pitch(LP);
   constexpr int NC = (LP + 1) * (LP + 2) * (LP + 3) / 6;
-  // scratch: my table entry times the powers of (x - xp); the coefficients
-  __syncwarp();
+  constexpr int NCL = (NC + 31) / 32;  // coefficient registers per lane
+  const int lane = c.lane;
+  __syncwarp();  // the previous run's scratch reads are complete
+
+  // ---- software pipeline: the next pair's table entry and coefficients are fetched
+  // while the current pair is processed.  The pipeline registers (e_n, roff_n, o_n,
+  // c_n) are CONSUMED (scratch stores) before the next fetch overwrites them and the
+  // pair records are re-read from L1 instead of being rotated through registers:
+  // ptxas 12.9 (-O1 and up) miscompiles "copy, then overwrite the source" rotations
+  // of loaded values in the large high-lp loop bodies -- later pairs of a run then
+  // see stale data (tests/test_b200_parity.py::test_multi_pair_items pins this).
+  double e_n, roff_n, c_n[NCL];
+  int o_n;
+#define B200_FETCH(R)                                                          \
+  {                                                                            \
+    o_n = sext_byte(R.z, c.sel);                                               \
+    const int ge_ = min(max(c.gbias - o_n, 0), c.ge_max);                      \
+    const double *row_ = c.etab_axis + (size_t)R.x * (unsigned)c.row3;         \
+    roff_n = __ldg(row_);                                                      \
+    e_n = __ldg(row_ + 1 + ge_);                                               \
+    if (COLLOCATE) {                                                           \
+      const double *c_ = c.coef_lane + ((int)R.x - c.tt_first) * c.coef_stride; \
+      _Pragma("unroll") for (int k = 0; k < NCL; k++)                          \
+        c_n[k] = (lane + 32 * k < NC) ? c_[32 * k] : 0.0;                      \
+    }                                                                          \
+  }
   {
-    double v = e;
-    double *row = ws + lane * PITCH;
-#pragma unroll
-    for (int l = 0; l <= LP; l++) {
-      row[l] = v;
-      v *= x;
-    }
-    if (COLLOCATE) {
-#pragma unroll
-      for (int k = 0; k < NCL; k++)
-        if (lane + 32 * k < NC)
-          ws[32 * PITCH + lane + 32 * k] = creg[k];
-    }
-  }
-  __syncwarp();
-
-  const double *__restrict__ tZ = ws + 16 * PITCH;
-  const double *__restrict__ C = ws + 32 * PITCH;
-  double X[LP + 1], Y0[LP + 1], Y1[LP + 1];
-#pragma unroll
-  for (int l = 0; l <= LP; l++) {
-    X[l] = ws[li * PITCH + l];
-    Y0[l] = ws[(8 + lj) * PITCH + l];
-    Y1[l] = ws[(12 + lj) * PITCH + l];
+    const uint4 Rf = c.pairs[first];
+    B200_FETCH(Rf)
   }
 
-  if (COLLOCATE) {
-    // E[ly][lz] = sum_lx C[lx,ly,lz] X[lx]  (shared by both columns: same x)
-    // D_c[lz]   = sum_ly E[ly][lz] Y_c[ly]
-    double D0[LP + 1], D1[LP + 1];
+  for (int ip = first; ip < last; ip++) {
+    const uint4 R0 = c.pairs[ip];                        // L1 hit (read as Rn one iteration ago)
+    const uint4 Rn = c.pairs[min(ip + 1, last - 1)];     // same line 7 times out of 8
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(c.pairs + min(ip + 8, last - 1)));
+
+    // scratch: my table entry times the powers of (x - xp); the coefficients
+    double *ws = c.ws + (ip & 1) * STAGE;
+    {
+      const double x = (double)(c.my_t - o_n) * c.my_h - roff_n;
+      double *row = ws + lane * PITCH;
+      if constexpr (LP == 0) {
+        row[0] = e_n;
+      } else {
+        double v0 = e_n;
 #pragma unroll
-    for (int lz = 0; lz <= LP; lz++)
-      D0[lz] = 0.0, D1[lz] = 0.0;
+        for (int l = 0; l + 1 <= LP; l += 2) {
+          const double v1 = v0 * x;
+          *reinterpret_cast<double2 *>(row + l) = make_double2(v0, v1);
+          v0 = v1 * x;
+        }
+        if constexpr ((LP & 1) == 0)
+          row[LP] = v0;
+      }
+      if (COLLOCATE) {
 #pragma unroll
-    for (int ly = 0; ly <= LP; ly++) {
-#pragma unroll
-      for (int lz = 0; lz <= LP - ly; lz++) {
-        double ev = C[coset(0, ly, lz)] * X[0];
-#pragma unroll
-        for (int lx = 1; lx <= LP - ly - lz; lx++)
-          ev = fma(C[coset(lx, ly, lz)], X[lx], ev);
-        D0[lz] = fma(ev, Y0[ly], D0[lz]);
-        D1[lz] = fma(ev, Y1[ly], D1[lz]);
+        for (int k = 0; k < NCL; k++)
+          if (lane + 32 * k < NC)
+            ws[32 * PITCH + lane + 32 * k] = c_n[k];
       }
     }
-#define B200_BODY(p)                                                           \
-  {                                                                            \
-    double z[LP + 1];                                                          \
-    _Pragma("unroll") for (int l = 0; l <= LP; l++) z[l] = tZ[(p)*PITCH + l];  \
-    double v0 = acc0[p], v1 = acc1[p];                                         \
-    _Pragma("unroll") for (int l = 0; l <= LP; l++) {                          \
-      v0 = fma(D0[l], z[l], v0);                                               \
-      v1 = fma(D1[l], z[l], v1);                                               \
-    }                                                                          \
-    acc0[p] = (mask0 & (1u << (p))) ? v0 : acc0[p];                            \
-    acc1[p] = (mask1 & (1u << (p))) ? v1 : acc1[p];                            \
-  }
-    B200_PLANES(B200_BODY)
-#undef B200_BODY
-  } else {
-    double S0[LP + 1], S1[LP + 1];
+    // (the tail re-fetches the last pair: harmless, and the loop stays branch-free)
+    B200_FETCH(Rn)
+
+    // sphere masks of my two columns: K+1 from the sphere table, then the plane mask
+    const unsigned char *kp = c.ktab_lane + R0.y;
+    const unsigned k0 = __ldg(kp), k1 = __ldg(kp + 4 * kKPitch);
+    const int ozb = sext_byte(R0.z, 16u);  // oz; the table pointer is biased
+    const unsigned mask0 = c.s_zm[(int)(k0 * kZmPitch) + ozb];
+    const unsigned mask1 = c.s_zm[(int)(k1 * kZmPitch) + ozb];
+    const int wlo = (int)((R0.z >> 24) & 15u), whi = (int)(R0.z >> 28);
+    __syncwarp();
+
+    const double *tZ = ws + 16 * PITCH;
+    double X[LP + 1], Y0[LP + 1], Y1[LP + 1];
+    load_row<LP>(ws + c.li * PITCH, X);
+    load_row<LP>(ws + (8 + c.lj) * PITCH, Y0);
+    load_row<LP>(ws + (12 + c.lj) * PITCH, Y1);
+
+    if (COLLOCATE) {
+      // E[ly][lz] = sum_lx C[lx,ly,lz] X[lx]  (shared by both columns: same x)
+      // D_c[lz]   = sum_ly E[ly][lz] Y_c[ly]
+      const double *C = ws + 32 * PITCH;
+      double D0[LP + 1], D1[LP + 1];
 #pragma unroll
-    for (int l = 0; l <= LP; l++)
-      S0[l] = 0.0, S1[l] = 0.0;
-#define B200_BODY(p)                                                           \
-  {                                                                            \
-    double z[LP + 1];                                                          \
-    _Pragma("unroll") for (int l = 0; l <= LP; l++) z[l] = tZ[(p)*PITCH + l];  \
-    const double a0 = (mask0 & (1u << (p))) ? acc0[p] : 0.0;                   \
-    const double a1 = (mask1 & (1u << (p))) ? acc1[p] : 0.0;                   \
-    _Pragma("unroll") for (int l = 0; l <= LP; l++) {                          \
-      S0[l] = fma(a0, z[l], S0[l]);                                            \
-      S1[l] = fma(a1, z[l], S1[l]);                                            \
-    }                                                                          \
-  }
-    B200_PLANES(B200_BODY)
-#undef B200_BODY
-    // table entries outside the cube are zero and inactive columns have S = 0:
-    // nothing spurious enters the warp-wide sums
-    if constexpr (LP <= 3) {
-      // few coefficients: one transposing reduction over all of them
-      double part[NC];
+      for (int lz = 0; lz <= LP; lz++)
+        D0[lz] = 0.0, D1[lz] = 0.0;
 #pragma unroll
       for (int ly = 0; ly <= LP; ly++) {
 #pragma unroll
         for (int lz = 0; lz <= LP - ly; lz++) {
-          const double w = fma(Y0[ly], S0[lz], Y1[ly] * S1[lz]);
+          double ev = C[coset(0, ly, lz)] * X[0];
 #pragma unroll
-          for (int lx = 0; lx <= LP - ly - lz; lx++)
-            part[coset(lx, ly, lz)] = X[lx] * w;
+          for (int lx = 1; lx <= LP - ly - lz; lx++)
+            ev = fma(C[coset(lx, ly, lz)], X[lx], ev);
+          D0[lz] = fma(ev, Y0[ly], D0[lz]);
+          D1[lz] = fma(ev, Y1[ly], D1[lz]);
         }
       }
-      const int idx = WarpVecReduce<NC>::run(part, lane);
-      if ((lane & (DupLanes<NC>::value - 1)) == 0 && idx < NC && part[0] != 0.0)
-        atomicAdd(&gcoef[idx], part[0]);
+#define B200_BODY(p)                                                           \
+  {                                                                            \
+    double z[LP + 1];                                                          \
+    load_row<LP>(tZ + (p)*PITCH, z);                                           \
+    PFma<LP>::col(acc0[p], D0, z, mask0 & (1u << (p)));                        \
+    PFma<LP>::col(acc1[p], D1, z, mask1 & (1u << (p)));                        \
+  }
+      B200_PLANES(B200_BODY)
+#undef B200_BODY
     } else {
-      IntegrateReduce<LP>::template slice<0>(X, Y0, Y1, S0, S1, gcoef, lane);
+      double S0[LP + 1], S1[LP + 1];
+#pragma unroll
+      for (int l = 0; l <= LP; l++)
+        S0[l] = 0.0, S1[l] = 0.0;
+#define B200_BODY(p)                                                           \
+  {                                                                            \
+    double z[LP + 1];                                                          \
+    load_row<LP>(tZ + (p)*PITCH, z);                                           \
+    PFma<LP>::integ(S0, acc0[p], z, mask0 & (1u << (p)));                      \
+    PFma<LP>::integ(S1, acc1[p], z, mask1 & (1u << (p)));                      \
+  }
+      B200_PLANES(B200_BODY)
+#undef B200_BODY
+      // table entries outside the cube are zero and inactive columns have S = 0:
+      // nothing spurious enters the warp-wide sums
+      double *__restrict__ gcoef = c.coef0 + ((int)R0.x - c.tt_first) * c.coef_stride;
+      if constexpr (LP <= 3) {
+        // few coefficients: one transposing reduction over all of them
+        double part[NC];
+#pragma unroll
+        for (int ly = 0; ly <= LP; ly++) {
+#pragma unroll
+          for (int lz = 0; lz <= LP - ly; lz++) {
+            const double w = fma(Y0[ly], S0[lz], Y1[ly] * S1[lz]);
+#pragma unroll
+            for (int lx = 0; lx <= LP - ly - lz; lx++)
+              part[coset(lx, ly, lz)] = X[lx] * w;
+          }
+        }
+        const int idx = WarpVecReduce<NC>::run(part, lane);
+        if ((lane & (DupLanes<NC>::value - 1)) == 0 && idx < NC && part[0] != 0.0)
+          atomicAdd(&gcoef[idx], part[0]);
+      } else {
+        IntegrateReduce<LP>::template slice<0>(X, Y0, Y1, S0, S1, gcoef, lane);
+      }
     }
   }
+#undef B200_FETCH
 }
 
 template <bool COLLOCATE, int LPLO, int LPHI>
 __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kernel(const TiledArgs A) {
   extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NCHI = (LPHI + 1) * (LPHI + 2) * (LPHI + 3) / 6;
-  constexpr int NCL = (NCHI + 31) / 32;  // coefficient registers per lane
-  constexpr int kScratch = 32 * (LPHI + 1) + NCHI;
-  double *ws = smem + (size_t)warp * kScratch;
-  int4 *s_khead = (int4 *)(smem + (size_t)kTiledWarps * kScratch);
-  signed char *s_ktab = (signed char *)(s_khead + (A.max_n + 1));
-  for (int q = tid; q <= A.max_n; q += kTiledThreads)
-    s_khead[q] = ((const int4 *)A.khead)[q];
-  for (int q = tid; q < (A.ktab_bytes + 15) / 16; q += kTiledThreads)
-    ((int4 *)s_ktab)[q] = ((const int4 *)A.ktab)[q];
+  constexpr int STAGE = stage_doubles(LPHI);
+  unsigned short *s_zm = (unsigned short *)(smem + (size_t)kTiledWarps * 2 * STAGE);
+  for (int q = tid; q < kZmRows * kZmPitch / 2; q += kTiledThreads)
+    ((unsigned *)s_zm)[q] = ((const unsigned *)A.zmask)[q];
   __syncthreads();  // the only CTA-wide barrier
+
+  LaneCtx c;
+  c.lane = lane, c.li = lane & 7, c.lj = lane >> 3;  // my columns: (li, lj) and (li, lj + 4)
+  // which table entry this lane fetches: axis and block-local index
+  const int my_axis = (lane < 8) ? 0 : ((lane < 16) ? 1 : 2);
+  c.my_t = (lane < 8) ? lane : ((lane < 16) ? lane - 8 : lane - 16);
+  c.my_h = (my_axis == 0) ? A.hx : ((my_axis == 1) ? A.hy : A.hz);
+  c.sel = 8u * my_axis;
+  c.row3 = 3 * A.P;
+  c.etab_axis = A.etab + my_axis * A.P;
+  c.gbias = c.my_t + A.max_nb + 1;  // etab entry index = gbias - o
+  c.ge_max = A.P - 2;
+  c.coef0 = A.coef + A.coef_base;
+  c.coef_lane = c.coef0 + lane;
+  c.tt_first = A.tt_first, c.coef_stride = A.coef_stride;
+  c.pairs = (const uint4 *)A.pairs;
+  c.ktab_lane = A.ktab + c.lj * kKPitch + c.li;
+  c.s_zm = s_zm + kZmBias;
+  c.ws = smem + (size_t)warp * 2 * STAGE;
 
   // persistent warps: work items are handed out in spatial order
   for (;;) {
-  int iw = 0;
-  if (lane == 0)
-    iw = atomicAdd(A.counter, 1);
-  iw = __shfl_sync(0xffffffffu, iw, 0);
-  if (iw >= A.nwork)
-    break;
-  const TWork W = A.work[iw];
-  const int vx = min(kBX, A.nx - W.x0), vy = min(kBY, A.ny - W.y0), vz = min(kBZ, A.nz - W.z0);
-  const int li = lane & 7, lj = lane >> 3;  // my columns: (li, lj) and (li, lj + 4)
-  const size_t sy = A.nx, sz = (size_t)A.nx * A.ny;
-  double *g0 = A.grid + (size_t)W.z0 * sz + (size_t)(W.y0 + lj) * sy + W.x0 + li;
-  double *g1 = g0 + 4 * sy;
-  const bool col0 = (li < vx && lj < vy), col1 = (li < vx && lj + 4 < vy);
-  const unsigned vzmask = (vz >= 16) ? 0xffffu : ((1u << vz) - 1u);
-
-  double acc0[kBZ], acc1[kBZ];
-#pragma unroll
-  for (int p = 0; p < kBZ; p++) {
-    acc0[p] = 0.0, acc1[p] = 0.0;
-    if (!COLLOCATE && p < vz) {
-      if (col0)
-        acc0[p] = g0[p * sz];
-      if (col1)
-        acc1[p] = g1[p * sz];
-    }
-  }
-
-  // which table entry this lane fetches: axis and block-local index
-  const int my_axis = (lane < 8) ? 0 : ((lane < 16) ? 1 : 2);
-  const int my_t = (lane < 8) ? lane : ((lane < 16) ? lane - 8 : lane - 16);
-  const double my_h = (my_axis == 0) ? A.hx : ((my_axis == 1) ? A.hy : A.hz);
-  const int oshift = 24 - 8 * my_axis;           // sign-extending extraction of o[my_axis]
-  const int row3 = 3 * A.P;
-  const double *__restrict__ etab_axis = A.etab + my_axis * A.P;
-  const int gbias = my_t + A.max_nb + 1;         // etab entry index = gbias - o
-  const int ge_max = A.P - 2;
-  const double *__restrict__ coef_lane = A.coef + A.coef_base + lane;
-
-  // ---- software pipeline: fetch(pair ip+1) while processing pair ip -----------
-  const uint2 *__restrict__ pairs2 = (const uint2 *)A.pairs;
-  uint2 Pn = pairs2[W.first];
-  uint2 Pnn = pairs2[min(W.first + 1, W.last - 1)];
-  double e_n, roff_n, c_n[NCL];
-  int o_n;
-#define B200_FETCH()                                                           \
-  {                                                                            \
-    const int q_ = (int)(Pn.x & 0x1fffffu);                                    \
-    const double *row_ = etab_axis + q_ * row3;                                \
-    o_n = ((int)(Pn.y << oshift)) >> 24;                                       \
-    const int ge_ = min(max(gbias - o_n, 0), ge_max);                          \
-    roff_n = row_[0];                                                          \
-    e_n = row_[1 + ge_];                                                       \
-    if (COLLOCATE) {                                                           \
-      const double *c_ = coef_lane + (q_ - A.tt_first) * A.coef_stride;        \
-      _Pragma("unroll") for (int k = 0; k < NCL; k++)                          \
-        c_n[k] = (lane + 32 * k < NCHI) ? c_[32 * k] : 0.0;                    \
-    }                                                                          \
-  }
-  B200_FETCH()
-
-  for (int ip = W.first; ip < W.last; ip++) {
-    const uint2 P = Pn;
-    const double e = e_n, roff = roff_n;
-    double creg[NCL];
-#pragma unroll
-    for (int k = 0; k < NCL; k++)
-      creg[k] = COLLOCATE ? c_n[k] : 0.0;
-    const int o_mine = o_n;
-    if (ip + 1 < W.last) {
-      Pn = Pnn;  // record fetched one iteration ago: its dependent loads start now
-      B200_FETCH()
-      Pnn = pairs2[min(ip + 2, W.last - 1)];
-    }
-    const int lp = (int)(P.x >> 27) + A.dl;
-    const int ox = ((int)(P.y << 24)) >> 24, oy = ((int)(P.y << 16)) >> 24, oz = ((int)(P.y << 8)) >> 24;
-
-    // admissible planes of my two columns, as 16-bit masks
-    const int4 H = s_khead[(P.x >> 21) & 63u];  // offset, nbx, nby, nbz
-    const int wx = 2 * H.y + 2;
-    const unsigned ti = (unsigned)(li - ox + H.y);
-    unsigned mask[2];
-#pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const unsigned tj = (unsigned)(lj + 4 * c - oy + H.z);
-      int K = -1;
-      if (ti < (unsigned)wx && tj < (unsigned)(2 * H.z + 2) && (c == 0 ? col0 : col1))
-        K = s_ktab[H.x + (int)tj * wx + (int)ti];
-      // planes p with pair_dist(p - oz) <= K  <=>  oz - K <= p <= oz + K + 1
-      const int plo = max(oz - K, 0), phi = min(oz + K + 1, 15);
-      mask[c] = (K >= 0 && plo <= phi) ? (((2u << (phi - plo)) - 1u) << plo) & vzmask : 0u;
-    }
-    const unsigned wmask = __reduce_or_sync(0xffffffffu, mask[0] | mask[1]);
-    if (wmask == 0u)
-      continue;  // warp-uniform: the sphere misses this block after all
-    const int wlo = __ffs(wmask) - 1, whi = 31 - __clz(wmask);
-    const double x = (my_t - o_mine) * my_h - roff;
-    double *gcoef = A.coef + A.coef_base + ((int)(P.x & 0x1fffffu) - A.tt_first) * A.coef_stride;
-
-    switch (lp) {
-#define B200_CASE(LPV)                                                                             \
-  case LPV:                                                                                        \
-    if constexpr (LPV >= LPLO && LPV <= LPHI)                                                      \
-      process_pair<COLLOCATE, LPV, NCL>(ws, gcoef, e, x, creg, mask[0], mask[1], wlo, whi, li, lj, \
-                                        lane, acc0, acc1);                                         \
-    break;
-      B200_CASE(0)
-      B200_CASE(1)
-      B200_CASE(2)
-      B200_CASE(3)
-      B200_CASE(4)
-      B200_CASE(5)
-      B200_CASE(6)
-#undef B200_CASE
-    default:
+    int iw = 0;
+    if (lane == 0)
+      iw = atomicAdd(A.counter, 1);
+    iw = __shfl_sync(0xffffffffu, iw, 0);
+    if (iw >= A.nwork)
       break;
-    }
-  }
+    const int4 W0 = ((const int4 *)A.work)[2 * iw], W1 = ((const int4 *)A.work)[2 * iw + 1];
+    const int x0 = W0.x, y0 = W0.y, z0 = W0.z;
+    const int vx = min(kBX, A.nx - x0), vy = min(kBY, A.ny - y0), vz = min(kBZ, A.nz - z0);
+    const size_t sy = A.nx, sz = (size_t)A.nx * A.ny;
+    double *g0 = A.grid + (size_t)z0 * sz + (size_t)(y0 + c.lj) * sy + x0 + c.li;
+    double *g1 = g0 + 4 * sy;
+    const bool col0 = (c.li < vx && c.lj < vy), col1 = (c.li < vx && c.lj + 4 < vy);
 
-  if (COLLOCATE) {
+    // Points outside the grid (partial edge blocks) need no masking in the pair
+    // loops: they integrate zeros and their collocated values are never flushed.
+    double acc0[kBZ], acc1[kBZ];
 #pragma unroll
     for (int p = 0; p < kBZ; p++) {
-      if (p < vz) {
-        if (col0 && acc0[p] != 0.0)
-          atomicAdd(&g0[p * sz], acc0[p]);
-        if (col1 && acc1[p] != 0.0)
-          atomicAdd(&g1[p * sz], acc1[p]);
+      acc0[p] = 0.0, acc1[p] = 0.0;
+      if (!COLLOCATE && p < vz) {
+        if (col0)
+          acc0[p] = g0[p * sz];
+        if (col1)
+          acc1[p] = g1[p * sz];
       }
     }
-  }
+
+    run_pairs<COLLOCATE, LPLO, STAGE>(c, W0.w, W1.x, acc0, acc1);
+    if constexpr (LPLO + 1 <= LPHI)
+      run_pairs<COLLOCATE, LPLO + 1, STAGE>(c, W1.x, W1.y, acc0, acc1);
+    if constexpr (LPLO + 2 <= LPHI)
+      run_pairs<COLLOCATE, LPLO + 2, STAGE>(c, W1.y, W1.z, acc0, acc1);
+
+    if (COLLOCATE) {
+#pragma unroll
+      for (int p = 0; p < kBZ; p++) {
+        if (p < vz) {
+          if (col0 && acc0[p] != 0.0)
+            atomicAdd(&g0[p * sz], acc0[p]);
+          if (col1 && acc1[p] != 0.0)
+            atomicAdd(&g1[p * sz], acc1[p]);
+        }
+      }
+    }
   }  // work items
-#undef B200_FETCH
 }
 
-inline size_t tiled_smem_bytes(const int lphi, const int max_n, const int ktab_bytes) {
-  const size_t nd = (size_t)kTiledWarps * (32 * (lphi + 1) + ncoset(lphi));
-  return nd * sizeof(double) + (max_n + 1) * sizeof(KTabHeader) + ktab_bytes + 32;
+inline size_t tiled_smem_bytes(const int lphi) {
+  return (size_t)kTiledWarps * 2 * stage_doubles(lphi) * sizeof(double) +
+         (size_t)kZmRows * kZmPitch * sizeof(unsigned short);
 }
 
 template <bool COLLOCATE, int LPLO, int LPHI>
 inline void launch_tiled_class(const TiledArgs &A, const TiledLevel &tl, cudaStream_t s) {
-  const size_t bytes = tiled_smem_bytes(LPHI, tl.max_n, tl.ktab_bytes);
+  (void)tl;
+  const size_t bytes = tiled_smem_bytes(LPHI);
   B200_ASSERT(bytes <= 200 * 1024, "tiled kernel: shared memory budget exceeded");
   B200_CHECK(cudaFuncSetAttribute(tiled_kernel<COLLOCATE, LPLO, LPHI>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -872,12 +921,11 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
   B200_ASSERT(L.dl >= 0 && L.dl < 8, "unexpected l growth");
   TiledArgs A;
   A.pairs = tl.d_pairs;
-  A.khead = tl.d_khead, A.ktab = tl.d_ktab, A.ktab_bytes = tl.ktab_bytes, A.max_n = tl.max_n;
+  A.ktab = tl.d_ktab, A.zmask = tl.d_zmask;
   A.etab = tl.d_etab, A.P = tl.P, A.max_nb = tl.max_nb;
   A.coef = L.coef, A.grid = L.grid;
   A.nx = L.level.npts_local[0], A.ny = L.level.npts_local[1], A.nz = L.level.npts_local[2];
   A.hx = L.level.dh[0], A.hy = L.level.dh[4], A.hz = L.level.dh[8];
-  A.dl = L.dl;
   unsigned leftover = 0u;
   B200_CHECK(cudaMemsetAsync(tl.d_counters + (COLLOCATE ? 0 : kNumClasses), 0, kNumClasses * sizeof(int),
                              L.stream));
@@ -904,7 +952,6 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
     else if (lo == 4 && hi == 6) launch_tiled_class<COLLOCATE, 4, 6>(A, tl, s);
     else if (lo == 4) launch_tiled_class<COLLOCATE, 4, 5>(A, tl, s);
     else if (lo == 5) launch_tiled_class<COLLOCATE, 5, 6>(A, tl, s);
-    else if (lo == 6) launch_tiled_class<COLLOCATE, 6, 6>(A, tl, s);
     else leftover |= 1u << cls;
   }
   return leftover;

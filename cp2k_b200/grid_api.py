@@ -308,6 +308,9 @@ _B200 = None
 
 
 def lib_path() -> str:
+    override = os.environ.get("GRID_B200_LIB")  # an alternative build of the same library (debugging)
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libgrid_b200.so")
 
 

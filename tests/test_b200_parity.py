@@ -195,3 +195,43 @@ def test_stats_match_oracle_counters(b200, oracle, wl_ortho, wl_general):
         c = oracle.counters()
         assert st["npts_model"] == c["npts"]
         assert abs(st["flops_collocate"] - c["flops"]) <= 1e-9 * c["flops"]
+
+
+def _lp0_of(wl):
+    t, kinds = wl.tasks, wl.atom_kinds
+    lmax = [np.asarray(b.lmax) for b in wl.basis_sets]
+    la = np.array([lmax[kinds[a - 1] - 1][s - 1] for a, s in zip(t["iatom_list"], t["iset_list"])])
+    lb = np.array([lmax[kinds[a - 1] - 1][s - 1] for a, s in zip(t["jatom_list"], t["jset_list"])])
+    return la + lb
+
+
+@pytest.mark.parametrize("lp0", [0, 1, 2, 3, 4])
+def test_multi_pair_items(b200, oracle, wl_ortho, lp0):
+    """Several (task, block) pairs per work item in every lp-specialised pair
+    loop of the tiled kernels: the same task repeated (identical geometry, so
+    every block sees it several times) plus a few different ones, for every l
+    growth the API can ask for (collocate dl = 0, 1, 2; integrate dl = 0..3)."""
+    ids = np.nonzero(_lp0_of(wl_ortho) == lp0)[0]
+    if ids.size == 0:
+        pytest.skip("no such tasks in the synthetic workload")
+    sel = np.array([ids[0]] * 3 + list(ids[:5]))
+    wl = wl_ortho.subset(sel)
+    pab = wl.random_pab(8)
+    for func in (100, 301, 200):
+        ref = _collocate(oracle, wl, func, pab)
+        got = _collocate(b200, wl, func, pab)
+        for a, b in zip(got, ref):
+            assert rel_diff(a, b) < GRID_TOL, (func, lp0)
+    grids = wl.new_grids()
+    rng = np.random.default_rng(9)
+    for g in grids:
+        g.host[:] = rng.normal(size=g.host.size)
+    for tau in (False, True):
+        for fv in ((False, False), (True, False), (True, True)):
+            hab_r, f_r, v_r = _integrate(oracle, wl, tau, pab, grids, *fv)
+            hab_g, f_g, v_g = _integrate(b200, wl, tau, pab, grids, *fv)
+            assert rel_diff(hab_g, hab_r) < HAB_TOL, (tau, fv, lp0)
+            if fv[0]:
+                assert rel_diff(f_g, f_r) < FV_TOL
+            if fv[1]:
+                assert rel_diff(v_g, v_r) < FV_TOL
