@@ -236,8 +236,8 @@ __device__ inline void make_alpha(const TaskDev &T, const int la_c,
 // pab_to_coef: one warp per task.
 // ---------------------------------------------------------------------------
 struct CoefDims {
-  int work, raw, cab, alpha, cxyz, part;  // doubles per warp
-  __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz + part; }
+  int work, raw, cab, alpha, cxyz;  // doubles per warp
+  __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz; }
 };
 
 // Tasks are tiny: a group of kCoefGroup lanes (half a warp) handles one task, so
@@ -259,7 +259,6 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
   double *s_cab = s_raw + D.raw;
   double *s_alpha = s_cab + D.cab;
   double *s_cxyz = s_alpha + D.alpha;
-  double *s_part = s_cxyz + D.cxyz;
   auto sync = [gmask] { __syncwarp(gmask); };
 
   FuncDesc F;
@@ -271,7 +270,7 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
     const int la_c = T.la_max + F.dla_max, lb_c = T.lb_max + F.dlb_max;
     const int la_min_c = max(T.la_min + F.dla_min, 0);
     const int lb_min_c = max(T.lb_min + F.dlb_min, 0);
-    const int lp = la_c + lb_c, lp1 = lp + 1, nc = ncoset(lp);
+    const int lp = la_c + lb_c, nc = ncoset(lp);
     double *out = L.coef + L.coef_offsets[itask];
     if (T.skip) {
       for (int c = lane; c < nc; c += G)
@@ -316,40 +315,28 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
     const double pref = rscale * T.prefactor;
     const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
     const bool to_cijk = !T.use_ortho;
-    // two passes so that all lanes work: partial sums per (k, b), then over b
-    const int nbr = n2c - cb_lo;
-    const int cchunk = max(1, D.part / nbr);  // coefficients per pass (scratch size)
-    for (int c0 = 0; c0 < nc; c0 += cchunk) {
-    const int ncc = min(cchunk, nc - c0);
-    for (int q = lane; q < ncc * nbr; q += G) {
-      const int c = c0 + q / nbr, ib = cb_lo + q % nbr;
-      const Orb k = orb_of(s_orb, c), b = orb_of(s_orb, ib);
-      double acc = 0.0;
-      if (k.l[0] - b.l[0] <= la_c && k.l[1] - b.l[1] <= la_c && k.l[2] - b.l[2] <= la_c) {
-        for (int ia = ca_lo; ia < n1c; ia++) {
-          const Orb a = orb_of(s_orb, ia);
-          if (k.l[0] <= a.l[0] + b.l[0] && k.l[1] <= a.l[1] + b.l[1] &&
-              k.l[2] <= a.l[2] + b.l[2]) {
-            acc += s_cab[ib * n1c + ia] *
-                   (B200_AL(0, a.l[0], b.l[0], k.l[0]) *
-                    B200_AL(1, a.l[1], b.l[1], k.l[1]) *
-                    B200_AL(2, a.l[2], b.l[2], k.l[2]) * pref);
-          }
+    // Every output coefficient k walks the precomputed list of (a, b) pairs that
+    // reach it (b200_internal.cuh: GatherList) -- no tests, no index arithmetic.
+    // Outputs are dealt to the lanes longest list first.
+    {
+      const GatherList GLs = L.glists[la_c * (kMaxLSide + 1) + lb_c];
+      (void)ca_lo, (void)cb_lo;  // entries below the minimum l are zero in s_cab
+      for (int cc = lane; cc < nc; cc += G) {
+        const int c = GLs.kperm[cc];
+        double acc = 0.0;
+        const int e1 = GLs.kstart[c + 1];
+        for (int e = GLs.kstart[c]; e < e1; e++) {
+          const unsigned long long w = GLs.by_k[e];
+          acc += s_cab[(unsigned)(w & 0xffffu)] *
+                 (s_alpha[(unsigned)((w >> 16) & 0xffffu)] * s_alpha[(unsigned)((w >> 32) & 0xffffu)] *
+                  s_alpha[(unsigned)(w >> 48)]);
         }
+        acc *= pref;
+        if (to_cijk)
+          s_cxyz[c] = acc;
+        else
+          out[c] = acc;
       }
-      s_part[q] = acc;
-    }
-    __syncwarp(gmask);
-    for (int cc = lane; cc < ncc; cc += G) {
-      double acc = 0.0;
-      for (int j = 0; j < nbr; j++)
-        acc += s_part[cc * nbr + j];
-      if (to_cijk)
-        s_cxyz[c0 + cc] = acc;
-      else
-        out[c0 + cc] = acc;
-    }
-    __syncwarp(gmask);
     }
     if (to_cijk) {  // lattice-polynomial basis for the general path
       __syncwarp(gmask);
@@ -451,7 +438,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
     const int la_c = T.la_max + dla_max, lb_c = T.lb_max + dlb_max;
     const int la_min_c = max(T.la_min + dla_min, 0);
     const int lb_min_c = max(T.lb_min + dlb_min, 0);
-    const int lp = la_c + lb_c, lp1 = lp + 1, nc = ncoset(lp);
+    const int lp = la_c + lb_c, nc = ncoset(lp);
     const double *in = L.coef + L.coef_offsets[itask];
 
     // (1) coefficients, back to the Cartesian polynomial basis if needed
@@ -475,20 +462,23 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
     // (2) cab[b][a] = prefactor * sum_k cxyz[k] ax ay az
     const int n1c = ncoset(la_c), n2c = ncoset(lb_c);
     const int ca_lo = ncoset(la_min_c - 1), cb_lo = ncoset(lb_min_c - 1);
-    for (int q = lane; q < n1c * n2c; q += G) {
-      const int ia = q % n1c, ib = q / n1c;
-      double acc = 0.0;
-      if (ia >= ca_lo && ib >= cb_lo) {
-        const Orb a = orb_of(s_orb, ia), b = orb_of(s_orb, ib);
-        for (int kz = 0; kz <= a.l[2] + b.l[2]; kz++)
-          for (int ky = 0; ky <= a.l[1] + b.l[1]; ky++)
-            for (int kx = 0; kx <= a.l[0] + b.l[0]; kx++)
-              acc += s_cxyz[coset(kx, ky, kz)] *
-                     (B200_AL(0, a.l[0], b.l[0], kx) *
-                      B200_AL(1, a.l[1], b.l[1], ky) *
-                      B200_AL(2, a.l[2], b.l[2], kz) * T.prefactor);
+    {
+      const GatherList GLs = L.glists[la_c * (kMaxLSide + 1) + lb_c];
+      for (int q = lane; q < n1c * n2c; q += G) {
+        const int ia = q % n1c, ib = q / n1c;
+        double acc = 0.0;
+        if (ia >= ca_lo && ib >= cb_lo) {
+          const int e1 = GLs.abstart[q + 1];
+          for (int e = GLs.abstart[q]; e < e1; e++) {
+            const unsigned long long w = GLs.by_ab[e];
+            acc += s_cxyz[(unsigned)(w & 0xffffu)] *
+                   (s_alpha[(unsigned)((w >> 16) & 0xffffu)] * s_alpha[(unsigned)((w >> 32) & 0xffffu)] *
+                    s_alpha[(unsigned)(w >> 48)]);
+          }
+          acc *= T.prefactor;
+        }
+        s_cab[q] = acc;
       }
-      s_cab[q] = acc;
     }
     // (3) density sub-block for forces / virial
     if (do_f || do_v)
@@ -595,7 +585,6 @@ inline void launch_pab_to_coef(const CoefLaunch &L, const int func, const double
   D.cab = ncoset(max_la_c) * ncoset(max_lb_c);
   D.alpha = 3 * (max_la_c + 1) * (max_lb_c + 1) * (max_la_c + max_lb_c + 1);
   D.cxyz = ncoset(max_la_c + max_lb_c);
-  D.part = std::min(ncoset(max_la_c + max_lb_c) * ncoset(max_lb_c), std::max(1024, ncoset(max_lb_c)));
   const size_t per_group = (size_t)D.total() * sizeof(double);
   B200_ASSERT(per_group <= kSmemBudget, "basis too large for the coefficient kernel");
   // half-warp groups when two of them fit (small tasks), else one warp per task

@@ -107,6 +107,20 @@ struct OrbTable {
   unsigned char l[816][3];  // ncoset(15) = 816
 };
 
+// Index lists of the Cartesian <-> polynomial transform for one (la, lb) after
+// ldiffs (ref/grid_ref_collint.h:827-911): every (a, b, k) with k_d <= a_d + b_d,
+// once ordered by the polynomial index k (collocate: gather into C_xyz) and once
+// by the pair index ib * ncoset(la) + ia (integrate: gather into cab).  An entry
+// packs four 16-bit indices: [0] the other side's index (pair index resp. k),
+// [1..3] the positions of the three binomial factors in the task's alpha table.
+struct GatherList {
+  const unsigned long long *by_k;
+  const int *kstart;   // [ncoset(lp) + 1]
+  const int *kperm;    // outputs by decreasing list length
+  const unsigned long long *by_ab;
+  const int *abstart;  // [ncoset(la) * ncoset(lb) + 1]
+};
+
 // ---- launch bookkeeping ---------------------------------------------------
 void count_launch(int n = 1);
 
@@ -119,6 +133,7 @@ struct CoefLaunch {
   const int *coef_offsets; // per task (indexed by task id)
   double *coef;
   const double *const *cijk_T;  // per (level*(kMaxLp+1)+lp) transform or null
+  const GatherList *glists;     // [(kMaxLSide+1)^2], indexed la * (kMaxLSide+1) + lb
   cudaStream_t stream;
 };
 
@@ -131,6 +146,7 @@ struct HabLaunch {
   const int *coef_offsets;
   const double *coef;
   const double *const *cijk_T;
+  const GatherList *glists;
   const double *pab;            // may be null
   double *hab;
   double *forces;               // device [natoms][3] or null

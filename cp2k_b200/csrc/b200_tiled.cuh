@@ -38,6 +38,7 @@
 #include <cmath>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "b200_generic.cuh"
@@ -53,7 +54,7 @@ constexpr int kTiledMaxNb = 23;               // max cube half-width (sphere-tab
 constexpr int kTiledMaxN = 30;                // max discretised radius index
 constexpr int kKPitch = 64;                   // sphere-table row pitch (bytes)
 constexpr int kKPad = 8;                      // margin around the cube: block offsets need no bounds check
-constexpr int kZmPitch = 64;                  // plane-mask table: [K+1][oz + kZmBias]
+constexpr int kZmPitch = 66;                  // plane-mask table: [K+1][oz + kZmBias]; rows 33 banks apart
 constexpr int kZmBias = 24;
 constexpr int kZmRows = kTiledMaxNb + 2;
 constexpr int kLpBuckets = kTiledMaxLp + 1;
@@ -216,6 +217,8 @@ struct PairGenArgs {
   const unsigned int *bucket_start;  // pass 1
   unsigned int *bucket_cursor;    // pass 1
   TPair *pairs;                   // pass 1
+  unsigned long long *keys;       // pass 1: bucket << qbits | q, for the in-bucket ordering
+  int qbits;
 };
 
 __device__ inline int floor_div(const int a, const int b) {  // b > 0
@@ -289,6 +292,7 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
                         ((unsigned)wlo << 24) | ((unsigned)whi << 28);
                 P.pad = 0;
                 A.pairs[pos] = P;
+                A.keys[pos] = ((unsigned long long)bucket << A.qbits) | (unsigned long long)q;
               }
             }
           }
@@ -430,6 +434,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   PA.nbx = nbx, PA.nby = nby, PA.nbz = nbz, PA.nblocks = (unsigned)nblocks;
   PA.khead = tl.d_khead, PA.ktab = tl.d_ktab;
   PA.bucket_count = d_count, PA.bucket_start = d_start, PA.bucket_cursor = nullptr, PA.pairs = nullptr;
+  PA.keys = nullptr, PA.qbits = 0;
   const int pg_blocks = ((int)tt.size() + 127) / 128;
   pairgen_kernel<0><<<pg_blocks, 128, 0, s>>>(PA);
   B200_CHECK(cudaGetLastError());
@@ -447,10 +452,40 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   tl.npairs = (long long)npairs;
   B200_CHECK(cudaMalloc((void **)&tl.d_pairs, std::max<size_t>(npairs, 1) * sizeof(TPair)));
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
-  PA.bucket_cursor = d_count, PA.pairs = tl.d_pairs;
+  unsigned long long *d_keys[2] = {nullptr, nullptr};
+  TPair *d_pairs_alt = nullptr;
+  B200_CHECK(cudaMalloc((void **)&d_keys[0], std::max<size_t>(npairs, 1) * sizeof(unsigned long long)));
+  int qbits = 1, bbits = 1;
+  while (((size_t)1 << qbits) < tt.size())
+    qbits++;
+  while (((size_t)1 << bbits) < nbuckets)
+    bbits++;
+  PA.bucket_cursor = d_count, PA.pairs = tl.d_pairs, PA.keys = d_keys[0], PA.qbits = qbits;
   pairgen_kernel<1><<<pg_blocks, 128, 0, s>>>(PA);
   B200_CHECK(cudaGetLastError());
   count_launch(4);
+  // Order every bucket by task: neighbouring blocks then walk (nearly) the same
+  // tasks in the same order at the same time, so that the tasks' table rows and
+  // coefficients are shared through L1/L2 instead of being re-read from HBM; it
+  // also makes the accumulation order (and so the results) reproducible.
+  if (npairs > 1) {
+    B200_CHECK(cudaMalloc((void **)&d_keys[1], npairs * sizeof(unsigned long long)));
+    B200_CHECK(cudaMalloc((void **)&d_pairs_alt, npairs * sizeof(TPair)));
+    cub::DoubleBuffer<unsigned long long> kb(d_keys[0], d_keys[1]);
+    cub::DoubleBuffer<uint4> vb((uint4 *)tl.d_pairs, (uint4 *)d_pairs_alt);
+    void *d_sort_temp = nullptr;
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb, vb, (int)npairs, 0, qbits + bbits, s);
+    B200_CHECK(cudaMalloc(&d_sort_temp, std::max<size_t>(sort_bytes, 1)));
+    cub::DeviceRadixSort::SortPairs(d_sort_temp, sort_bytes, kb, vb, (int)npairs, 0, qbits + bbits, s);
+    B200_CHECK(cudaGetLastError());
+    B200_CHECK(cudaStreamSynchronize(s));
+    count_launch(6);
+    if ((TPair *)vb.Current() != tl.d_pairs)
+      std::swap(tl.d_pairs, d_pairs_alt);
+    cudaFree(d_sort_temp);
+  }
+  cudaFree(d_keys[0]), cudaFree(d_keys[1]), cudaFree(d_pairs_alt);
 
   // work items per lp class: a block's pairs of that class (contiguous, ordered by lp) cut into chunks
   std::vector<TWork> work;

@@ -157,6 +157,15 @@ struct TaskList {
   std::map<int, DevBuf<double>> Tmats;  // key = level*(kMaxLp+1)+lp
   std::vector<const double *> h_Tptrs;
   DevBuf<const double *> d_Tptrs;
+  // index lists of the cab <-> cxyz transform per (la, lb) after ldiffs
+  struct GatherBufs {
+    DevBuf<unsigned long long> by_k, by_ab;
+    DevBuf<int> kstart, kperm, abstart;
+  };
+  std::map<int, GatherBufs> gather_bufs;    // key = la * (kMaxLSide+1) + lb
+  std::vector<GatherList> h_glists;
+  DevBuf<GatherList> d_glists;
+  std::vector<std::pair<int, int>> l_combos;  // (la_max, lb_max) present in the list
   int max_nsgf_set = 1, max_ncoset_raw = 1, max_la = 0, max_lb = 0, maxco = 1;
   int max_block_size = 1;
   size_t pab_len = 0;
@@ -208,6 +217,13 @@ struct TaskList {
       kv.second.release();
     Tmats.clear();
     d_Tptrs.release();
+    for (auto &kv : gather_bufs) {
+      kv.second.by_k.release(), kv.second.by_ab.release();
+      kv.second.kstart.release(), kv.second.kperm.release(), kv.second.abstart.release();
+    }
+    gather_bufs.clear();
+    h_glists.clear();
+    d_glists.release();
     for (auto &li : linfo)
       li.tiled.release();
     for (int i = 0; i < 8; i++)
@@ -288,6 +304,67 @@ static void ensure_transforms(TaskList &tl, int dl, cudaStream_t s) {
   }
   if (changed)
     tl.d_Tptrs.upload(tl.h_Tptrs, s);
+}
+
+// Index lists of the Cartesian <-> polynomial transform (GatherList,
+// b200_internal.cuh) for every (la_max + dla, lb_max + dlb) this call meets.
+static void ensure_gather_lists(TaskList &tl, const int dla, const int dlb, cudaStream_t s) {
+  constexpr int W = kMaxLSide + 1;
+  if (tl.h_glists.empty())
+    tl.h_glists.assign((size_t)W * W, GatherList{nullptr, nullptr, nullptr, nullptr, nullptr});
+  bool changed = false;
+  for (const auto &lc : tl.l_combos) {
+    const int la = lc.first + dla, lb = lc.second + dlb;
+    B200_ASSERT(la <= kMaxLSide && lb <= kMaxLSide, "angular momentum too large");
+    const int key = la * W + lb;
+    if (tl.gather_bufs.count(key))
+      continue;
+    const int n1 = ncoset(la), n2 = ncoset(lb), lp = la + lb, lp1 = lp + 1, nc = ncoset(lp);
+    std::vector<int> lx(std::max(n1, n2)), ly(lx.size()), lz(lx.size());
+    for (int x = 0; x <= std::max(la, lb); x++)
+      for (int y = 0; x + y <= std::max(la, lb); y++)
+        for (int z = 0; x + y + z <= std::max(la, lb); z++) {
+          const int c = coset(x, y, z);
+          lx[c] = x, ly[c] = y, lz[c] = z;
+        }
+    auto AL = [&](int d, int a, int b, int k) { return (((d * (la + 1) + a) * (lb + 1) + b) * lp1) + k; };
+    B200_ASSERT(n1 * n2 < 65536 && AL(2, la, lb, lp) < 65536 && nc < 65536, "gather list index overflow");
+    std::vector<unsigned long long> by_ab;
+    std::vector<int> abstart(n1 * n2 + 1, 0);
+    std::vector<std::vector<unsigned long long>> per_k(nc);
+    for (int ib = 0; ib < n2; ib++)
+      for (int ia = 0; ia < n1; ia++) {
+        abstart[ib * n1 + ia] = (int)by_ab.size();
+        for (int kz = 0; kz <= lz[ia] + lz[ib]; kz++)
+          for (int ky = 0; ky <= ly[ia] + ly[ib]; ky++)
+            for (int kx = 0; kx <= lx[ia] + lx[ib]; kx++) {
+              const unsigned long long fac = ((unsigned long long)AL(0, lx[ia], lx[ib], kx) << 16) |
+                                             ((unsigned long long)AL(1, ly[ia], ly[ib], ky) << 32) |
+                                             ((unsigned long long)AL(2, lz[ia], lz[ib], kz) << 48);
+              const int k = coset(kx, ky, kz);
+              by_ab.push_back(fac | (unsigned long long)k);
+              per_k[k].push_back(fac | (unsigned long long)(ib * n1 + ia));
+            }
+      }
+    abstart[n1 * n2] = (int)by_ab.size();
+    std::vector<unsigned long long> by_k;
+    std::vector<int> kstart(nc + 1, 0), kperm(nc);
+    for (int k = 0; k < nc; k++) {
+      kstart[k] = (int)by_k.size();
+      by_k.insert(by_k.end(), per_k[k].begin(), per_k[k].end());
+      kperm[k] = k;
+    }
+    kstart[nc] = (int)by_k.size();
+    std::stable_sort(kperm.begin(), kperm.end(),
+                     [&](int a, int b) { return per_k[a].size() > per_k[b].size(); });
+    TaskList::GatherBufs &G = tl.gather_bufs[key];
+    G.by_k.upload(by_k, s), G.by_ab.upload(by_ab, s);
+    G.kstart.upload(kstart, s), G.kperm.upload(kperm, s), G.abstart.upload(abstart, s);
+    tl.h_glists[key] = GatherList{G.by_k.p, G.kstart.p, G.kperm.p, G.by_ab.p, G.abstart.p};
+    changed = true;
+  }
+  if (changed || tl.d_glists.p == nullptr)
+    tl.d_glists.upload(tl.h_glists, s);
 }
 
 // Coefficient buffer layout for one l growth `dl`.  Tasks on the tiled path
@@ -507,6 +584,9 @@ static void build_task_list(
     tl.max_nsgf_set = std::max({tl.max_nsgf_set, T.nsgf_seta, T.nsgf_setb});
     tl.max_ncoset_raw = std::max({tl.max_ncoset_raw, T.ncoseta, T.ncosetb});
     tl.max_la = std::max(tl.max_la, T.la_max);
+    if (std::find(tl.l_combos.begin(), tl.l_combos.end(), std::make_pair(T.la_max, T.lb_max)) ==
+        tl.l_combos.end())
+      tl.l_combos.push_back(std::make_pair(T.la_max, T.lb_max));
     tl.max_lb = std::max(tl.max_lb, T.lb_max);
     tl.max_block_size = std::max(tl.max_block_size, T.nsgfa * T.nsgfb);
   }
@@ -707,6 +787,7 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   const int dl = F.dla_max + F.dlb_max;
   ensure_coef_offsets(tl, dl, s);
   ensure_transforms(tl, dl, s);
+  ensure_gather_lists(tl, F.dla_max, F.dlb_max, s);
   tl.d_coef.ensure(tl.coef_total[dl]);
 
   // density blocks -> coefficients.  With host-authoritative buffers the upload
@@ -714,7 +795,7 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   CoefLaunch CL;
   CL.tasks = tl.d_tasks.p, CL.task_ids = nullptr, CL.ntasks = tl.ntasks;
   CL.sphi_pool = tl.d_sphi.p, CL.coef_offsets = tl.d_coef_off[dl].p, CL.coef = tl.d_coef.p;
-  CL.cijk_T = tl.d_Tptrs.p, CL.stream = s;
+  CL.cijk_T = tl.d_Tptrs.p, CL.glists = tl.d_glists.p, CL.stream = s;
   const double *d_pab = nullptr;
   if (g_device_resident && use_caller_device(pab_blocks)) {
     d_pab = pab_blocks->device_buffer;
@@ -836,6 +917,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   const int dl = dla_max + dlb_max;
   ensure_coef_offsets(tl, dl, s);
   ensure_transforms(tl, dl, s);
+  ensure_gather_lists(tl, dla_max, dlb_max, s);
   tl.d_coef.ensure(tl.coef_total[dl]);
   {  // the tiled integrate kernel accumulates into the coefficients
     ScopedTimer tm(T_MEMSET, s);
@@ -917,6 +999,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   HL.tasks = tl.d_tasks.p, HL.block_task_ids = tl.d_block_task_ids.p;
   HL.block_first = tl.d_block_first.p, HL.nblocks = tl.nblocks, HL.sphi_pool = tl.d_sphi.p;
   HL.coef_offsets = tl.d_coef_off[dl].p, HL.coef = tl.d_coef.p, HL.cijk_T = tl.d_Tptrs.p;
+  HL.glists = tl.d_glists.p;
   HL.pab = d_pab, HL.hab = d_hab;
   HL.forces = do_f ? tl.d_fv.p : nullptr;
   HL.virial = do_v ? tl.d_fv.p + (size_t)3 * natoms : nullptr;
