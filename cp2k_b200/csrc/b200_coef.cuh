@@ -181,21 +181,29 @@ __device__ inline void decontract_task(const TaskDev &T, const double *block,
                                        const int nthr, SyncF sync) {
   // raw[jco][ico] = sum_{sa,sb} sphi_b[sb][o2+jco] P(sa,sb) sphi_a[sa][o1+ico]
   const int na = T.ncoseta, nb = T.ncosetb;
-  const double *sphi_a = sphi_pool + T.sphi_a + T.sgfa * T.maxcoa + T.o1;
-  const double *sphi_b = sphi_pool + T.sphi_b + T.sgfb * T.maxcob + T.o2;
-  for (int q = t; q < T.nsgf_setb * na; q += nthr) {
-    const int sb = q / na, ico = q % na;
+  const int nsa = T.nsgf_seta, nsb = T.nsgf_setb, maxcoa = T.maxcoa, maxcob = T.maxcob;
+  const double *sphi_a = sphi_pool + T.sphi_a + T.sgfa * maxcoa + T.o1;
+  const double *sphi_b = sphi_pool + T.sphi_b + T.sgfb * maxcob + T.o2;
+  // element (sa, sb) of the sub-block = blk0[sa * str_a + sb * str_b]
+  const int str_a = T.transpose ? 1 : T.nsgfb, str_b = T.transpose ? T.nsgfa : 1;
+  const double *blk0 = block + (T.transpose ? T.sgfb * T.nsgfa + T.sgfa : T.sgfa * T.nsgfb + T.sgfb);
+  for (int q = t; q < nsb * na; q += nthr) {
+    const int sb = q / na, ico = q - sb * na;
+    const double *pb = blk0 + sb * str_b, *ps = sphi_a + ico;
     double acc = 0.0;
-    for (int sa = 0; sa < T.nsgf_seta; sa++)
-      acc += block_elem(T, block, sa, sb) * __ldg(&sphi_a[sa * T.maxcoa + ico]);
+#pragma unroll 4
+    for (int sa = 0; sa < nsa; sa++, pb += str_a, ps += maxcoa)
+      acc += __ldg(pb) * __ldg(ps);
     s_work[q] = acc;
   }
   sync();
   for (int q = t; q < nb * na; q += nthr) {
-    const int jco = q / na, ico = q % na;
+    const int jco = q / na, ico = q - jco * na;
+    const double *ps = sphi_b + jco, *pw = s_work + ico;
     double acc = 0.0;
-    for (int sb = 0; sb < T.nsgf_setb; sb++)
-      acc += __ldg(&sphi_b[sb * T.maxcob + jco]) * s_work[sb * na + ico];
+#pragma unroll 4
+    for (int sb = 0; sb < nsb; sb++, ps += maxcob, pw += na)
+      acc += __ldg(ps) * *pw;
     s_raw[q] = acc;
   }
   sync();
@@ -206,25 +214,30 @@ template <typename SyncF>
 __device__ inline void make_alpha(const TaskDev &T, const int la_c,
                                   const int lb_c, double *s_alpha, const int t,
                                   const int nthr, SyncF sync) {
+  // One lane per (d, lb): the rows la = 0..la_c follow from each other by one
+  // multiplication with (x - a) = (x - p) + pa.
   const int lp1 = la_c + lb_c + 1;
-  const int n = 3 * (la_c + 1) * (lb_c + 1);
+  const int n = 3 * (lb_c + 1);
   for (int q = t; q < n; q += nthr) {
-    const int lb = q % (lb_c + 1);
-    const int la = (q / (lb_c + 1)) % (la_c + 1);
-    const int d = q / ((lb_c + 1) * (la_c + 1));
+    const int lb = q % (lb_c + 1), d = q / (lb_c + 1);
     const double pa = T.rp[d] - T.ra[d];
     const double pb = T.rp[d] - (T.ra[d] + T.rab[d]);
-    double *al = s_alpha + q * lp1;
-    for (int k = 0; k < lp1; k++)
+    // la = 0: (x - b)^lb = sum_k binom(lb, k) pb^(lb-k) (x-p)^k, by repeated multiplication
+    double *al = s_alpha + ((d * (la_c + 1) + 0) * (lb_c + 1) + lb) * lp1;
+    al[0] = 1.0;
+    for (int k = 1; k < lp1; k++)
       al[k] = 0.0;
-    double pas = 1.0;  // pa^(la-s) built downwards from s = la
-    for (int s = la; s >= 0; s--) {
-      double pbt = 1.0;
-      for (int u = lb; u >= 0; u--) {
-        al[s + u] += c_binom[la][s] * pas * c_binom[lb][u] * pbt;
-        pbt *= pb;
-      }
-      pas *= pa;
+    for (int m = 1; m <= lb; m++)
+      for (int k = m; k >= 0; k--)
+        al[k] = ((k > 0) ? al[k - 1] : 0.0) + pb * al[k];
+    for (int la = 1; la <= la_c; la++) {
+      double *nx = s_alpha + ((d * (la_c + 1) + la) * (lb_c + 1) + lb) * lp1;
+      const int top = la + lb;
+      for (int k = lp1 - 1; k > top; k--)
+        nx[k] = 0.0;
+      for (int k = top; k >= 0; k--)
+        nx[k] = ((k > 0) ? al[k - 1] : 0.0) + pa * al[k];
+      al = nx;
     }
   }
   sync();
@@ -526,19 +539,23 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
     const double *sphi_a = L.sphi_pool + T.sphi_a + T.sgfa * T.maxcoa + T.o1;
     const double *sphi_b = L.sphi_pool + T.sphi_b + T.sgfb * T.maxcob + T.o2;
     for (int q = lane; q < T.nsgf_setb * na; q += G) {
-      const int sb = q / na, ico = q % na;
+      const int sb = q / na, ico = q - sb * na;
+      const double *ps = sphi_b + sb * T.maxcob, *ph = s_h + ico;
       double acc = 0.0;
-      for (int jco = 0; jco < nb; jco++)
-        acc += __ldg(&sphi_b[sb * T.maxcob + jco]) * s_h[jco * na + ico];
+#pragma unroll 4
+      for (int jco = 0; jco < nb; jco++, ps++, ph += na)
+        acc += __ldg(ps) * *ph;
       s_work[q] = acc;
     }
     __syncwarp(gmask);
     double *g_block = L.hab + T.block_offset;
     for (int q = lane; q < T.nsgf_seta * T.nsgf_setb; q += G) {
-      const int sa = q % T.nsgf_seta, sb = q / T.nsgf_seta;
+      const int sb = q / T.nsgf_seta, sa = q - sb * T.nsgf_seta;
+      const double *pw = s_work + sb * na, *ps = sphi_a + sa * T.maxcoa;
       double acc = 0.0;
+#pragma unroll 4
       for (int ico = 0; ico < na; ico++)
-        acc += s_work[sb * na + ico] * __ldg(&sphi_a[sa * T.maxcoa + ico]);
+        acc += pw[ico] * __ldg(ps + ico);
       if (acc != 0.0)
         atomicAdd(&g_block[block_index(T, sa, sb)], acc);
     }
