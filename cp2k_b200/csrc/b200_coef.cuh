@@ -164,6 +164,34 @@ __device__ inline int op_expand(const Op op, const Orb l, const double z,
 // ---------------------------------------------------------------------------
 // Shared building blocks (executed by `nthr` cooperating threads, rank `t`).
 // ---------------------------------------------------------------------------
+// The task record (360 bytes, read all over the kernels) of the NEXT task is
+// fetched into registers while the current task is processed and published
+// to shared memory at the top of the next iteration: the HBM latency of the
+// record (and of the task-id indirection) is off the critical path.
+constexpr int kTaskWords = (int)(sizeof(TaskDev) / 4);
+constexpr int kTaskDoubles = (int)((sizeof(TaskDev) + 7) / 8);
+static_assert(sizeof(TaskDev) % 4 == 0, "TaskDev is copied word-wise");
+template <int G> struct TaskPrefetch {
+  static constexpr int NW = (kTaskWords + G - 1) / G;
+  unsigned w[NW];
+  __device__ __forceinline__ void issue(const TaskDev *src, const int lane) {
+    const unsigned *p = reinterpret_cast<const unsigned *>(src);
+#pragma unroll
+    for (int k = 0; k < NW; k++)
+      w[k] = (lane + k * G < kTaskWords) ? __ldg(p + lane + k * G) : 0u;
+  }
+  __device__ __forceinline__ void commit(TaskDev *dst, const int lane) const {
+    unsigned *p = reinterpret_cast<unsigned *>(dst);
+#pragma unroll
+    for (int k = 0; k < NW; k++)
+      if (lane + k * G < kTaskWords)
+        p[lane + k * G] = w[k];
+  }
+};
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ inline double block_elem(const TaskDev &T, const double *block,
                                     const int sa, const int sb) {
   return T.transpose ? block[(T.sgfb + sb) * T.nsgfa + T.sgfa + sa]
@@ -250,7 +278,7 @@ __device__ inline void make_alpha(const TaskDev &T, const int la_c,
 // ---------------------------------------------------------------------------
 struct CoefDims {
   int work, raw, cab, alpha, cxyz;  // doubles per warp
-  __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz; }
+  __host__ __device__ int total() const { return work + raw + cab + alpha + cxyz + kTaskDoubles; }
 };
 
 // Tasks are tiny: a group of kCoefGroup lanes (half a warp) handles one task, so
@@ -272,14 +300,29 @@ pab_to_coef_kernel(const CoefLaunch L, const int func, const double *pab,
   double *s_cab = s_raw + D.raw;
   double *s_alpha = s_cab + D.cab;
   double *s_cxyz = s_alpha + D.alpha;
+  TaskDev *s_task = reinterpret_cast<TaskDev *>(s_cxyz + D.cxyz);
   auto sync = [gmask] { __syncwarp(gmask); };
 
   FuncDesc F;
   describe_func(func, F);
 
-  for (int it = blockIdx.x * wpc + warp; it < L.ntasks; it += gridDim.x * wpc) {
-    const int itask = L.task_ids ? L.task_ids[it] : it;
-    const TaskDev &T = L.tasks[itask];
+  TaskPrefetch<G> pf;
+  const int it0 = blockIdx.x * wpc + warp, stride = gridDim.x * wpc;
+  int id_next = 0;
+  if (it0 < L.ntasks) {
+    id_next = L.task_ids ? L.task_ids[it0] : it0;
+    pf.issue(L.tasks + id_next, lane);
+  }
+  for (int it = it0; it < L.ntasks; it += stride) {
+    const int itask = id_next;
+    __syncwarp(gmask);  // the previous task's reads of the record are complete
+    pf.commit(s_task, lane);
+    __syncwarp(gmask);
+    if (it + stride < L.ntasks) {
+      id_next = L.task_ids ? L.task_ids[it + stride] : it + stride;
+      pf.issue(L.tasks + id_next, lane);
+    }
+    const TaskDev &T = *s_task;
     const int la_c = T.la_max + F.dla_max, lb_c = T.lb_max + F.dlb_max;
     const int la_min_c = max(T.la_min + F.dla_min, 0);
     const int lb_min_c = max(T.lb_min + F.dlb_min, 0);
@@ -417,7 +460,7 @@ __device__ inline double vab_elem(const PCtx &p, const bool tau, const int what,
 
 struct HabDims {
   int work, raw, cab, alpha, cxyz, h;  // doubles per warp
-  __host__ __device__ int total() const { return work + raw + cab + alpha + 2 * cxyz + h; }
+  __host__ __device__ int total() const { return work + raw + cab + alpha + 2 * cxyz + h + kTaskDoubles; }
 };
 
 // One warp per task (tasks visited in block order for locality).  The spherical
@@ -440,12 +483,29 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
   double *s_cxyz = s_alpha + D.alpha;
   double *s_cijk = s_cxyz + D.cxyz;
   double *s_h = s_cijk + D.cxyz;
+  TaskDev *s_task = reinterpret_cast<TaskDev *>(s_h + D.h);
   auto sync = [gmask] { __syncwarp(gmask); };
   const bool do_f = (L.forces != nullptr), do_v = (L.virial != nullptr);
 
-  for (int it = blockIdx.x * wpc + warp; it < ntasks; it += gridDim.x * wpc) {
-    const int itask = L.block_task_ids[it];
-    const TaskDev &T = L.tasks[itask];
+  TaskPrefetch<G> pf;
+  const int it0 = blockIdx.x * wpc + warp, stride = gridDim.x * wpc;
+  int id_next = 0;
+  if (it0 < ntasks) {
+    id_next = L.block_task_ids[it0];
+    pf.issue(L.tasks + id_next, lane);
+  }
+  for (int it = it0; it < ntasks; it += stride) {
+    const int itask = id_next;
+    __syncwarp(gmask);  // the previous task's reads of the record are complete
+    pf.commit(s_task, lane);
+    __syncwarp(gmask);
+    if (it + stride < ntasks) {
+      id_next = L.block_task_ids[it + stride];
+      pf.issue(L.tasks + id_next, lane);
+      // its coefficients: up to G cache lines from the start of its slot
+      prefetch_l2(L.coef + L.coef_offsets[id_next] + 16 * lane);
+    }
+    const TaskDev &T = *s_task;
     if (T.skip)
       continue;
     const int la_c = T.la_max + dla_max, lb_c = T.lb_max + dlb_max;
@@ -608,14 +668,18 @@ inline void launch_pab_to_coef(const CoefLaunch &L, const int func, const double
   const int gpw = (8 * per_group <= kSmemBudget) ? 2 : 1;
   const int wpc = (int)std::min<size_t>(4, kSmemBudget / (per_group * gpw));
   const size_t bytes = per_group * gpw * wpc;
-  const int grid = std::min((L.ntasks + gpw * wpc - 1) / (gpw * wpc), 148 * 16);
+  // persistent CTAs (one wave): the per-CTA set-up (orbital table) is paid once per SM slot
+  auto grid_for = [&](auto kernel) {
+    B200_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int per_sm = 1;
+    B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * wpc, bytes));
+    return std::min((L.ntasks + gpw * wpc - 1) / (gpw * wpc), 148 * std::max(per_sm, 1));
+  };
   if (gpw == 2) {
-    B200_CHECK(cudaFuncSetAttribute(pab_to_coef_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)bytes));
+    const int grid = grid_for(pab_to_coef_kernel<16>);
     pab_to_coef_kernel<16><<<grid, 32 * wpc, bytes, L.stream>>>(L, func, pab, D);
   } else {
-    B200_CHECK(cudaFuncSetAttribute(pab_to_coef_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)bytes));
+    const int grid = grid_for(pab_to_coef_kernel<32>);
     pab_to_coef_kernel<32><<<grid, 32 * wpc, bytes, L.stream>>>(L, func, pab, D);
   }
   B200_CHECK(cudaGetLastError());
@@ -639,15 +703,18 @@ inline void launch_coef_to_hab(const HabLaunch &L, const int ntasks, const int m
   const int gpw = (8 * per_group <= kSmemBudget) ? 2 : 1;
   const int wpc = (int)std::min<size_t>(4, kSmemBudget / (per_group * gpw));
   const size_t bytes = per_group * gpw * wpc;
-  const int grid = std::min((ntasks + gpw * wpc - 1) / (gpw * wpc), 148 * 16);
+  auto grid_for = [&](auto kernel) {
+    B200_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    int per_sm = 1;
+    B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * wpc, bytes));
+    return std::min((ntasks + gpw * wpc - 1) / (gpw * wpc), 148 * std::max(per_sm, 1));
+  };
   if (gpw == 2) {
-    B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)bytes));
+    const int grid = grid_for(coef_to_hab_kernel<16>);
     coef_to_hab_kernel<16><<<grid, 32 * wpc, bytes, L.stream>>>(L, D, ntasks, dla_max, dla_min, dlb_max,
                                                                dlb_min);
   } else {
-    B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)bytes));
+    const int grid = grid_for(coef_to_hab_kernel<32>);
     coef_to_hab_kernel<32><<<grid, 32 * wpc, bytes, L.stream>>>(L, D, ntasks, dla_max, dla_min, dlb_max,
                                                                dlb_min);
   }
