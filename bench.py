@@ -32,6 +32,16 @@ sys.path.insert(0, ROOT)
 FP64_PEAK_TFLOPS = 36.1  # measured on this pool's B200 (profiles/microbench/mb.log, DFMA loop)
 
 
+def load_traffic(workload, direction):
+    """DRAM bytes per call of the grid kernels from the committed ncu capture
+    (profiles/r01/traffic_r01b.json); None for workloads that were not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic_r01b.json")))
+        return t[f"{direction}_bytes_per_call"] if t.get("workload") == workload else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -341,7 +351,8 @@ def main():
     roofline = {
         "bound": "fp64", "kernel": f"{dom} grid kernels (all levels of one call)",
         "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-        "frac": achieved_tf / FP64_PEAK_TFLOPS, "traffic": None,
+        "frac": achieved_tf / FP64_PEAK_TFLOPS,
+        "traffic": load_traffic(args.workload, dom) if world == 1 else None,
         "peak_source": "measured DFMA loop, profiles/microbench (MEASURED_PEAKS.json has no FP64 entry)",
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (dom_ms * 1e-3) * 1e-9 if dom_ms else 0,
                 "peak_gbs": peaks.get("hbm_gbs"), "of": "fallback" if peaks.get("_fallback") else "measured"},

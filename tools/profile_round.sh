@@ -1,17 +1,22 @@
-# Round profile (run under gpurun, ONE GPU): launch list of the bench command +
-# one full capture of the 16 tiled launches of one step + the coefficient kernels.
+# Round profile (run under gpurun, ONE GPU): the default bench line and the
+# reference arm, the ncu launch list of the bench command, one full capture of
+# the 16 tiled launches of one step and of the coefficient kernels.  The
+# .ncu-rep files are summarised on the box (they exceed gpurun's 64 MiB return
+# limit) and only the text/csv summaries come back.
 # Usage: bash tools/profile_round.sh <tag>
 cd $GRAFT_REPO_ROOT
 TAG=${1:-r01}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks_$TAG.csv &
-SMI=$!
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
-kill $SMI
+python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"tiled_kernel" -s 16 -c 16 -o gpurun_out/prof_$TAG -f \
+ncu --set full --clock-control none -k regex:"tiled_kernel" -s 16 -c 16 -o /tmp/prof_$TAG -f \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/prof_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"pab_to_coef|coef_to_hab" -s 12 -c 12 -o gpurun_out/prof_coef_$TAG -f \
+python tools/ncu_summary.py /tmp/prof_$TAG.ncu-rep > gpurun_out/ncu_tiled_$TAG.txt 2>&1
+ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_tiled_${TAG}_raw.csv 2>/dev/null
+ncu --set full --clock-control none -k regex:"pab_to_coef|coef_to_hab" -s 2 -c 2 -o /tmp/prof_coef_$TAG -f \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/prof_coef_$TAG.log 2>&1
-tail -c 400 gpurun_out/bench_$TAG.json
+python tools/ncu_summary.py /tmp/prof_coef_$TAG.ncu-rep > gpurun_out/ncu_coef_$TAG.txt 2>&1
+ncu -i /tmp/prof_coef_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_coef_${TAG}_raw.csv 2>/dev/null
+tail -c 300 gpurun_out/bench_$TAG.json; ls -la gpurun_out | tail -15
