@@ -249,6 +249,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # the NCCL version banner (NCCL_DEBUG=VERSION, also via /etc/nccl.conf) would precede
+        # the JSON line on stdout; an explicit NCCL_DEBUG=INFO etc. from the caller is kept
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = load_b200()
     lib.set_device(local_rank)
@@ -366,13 +370,28 @@ def main():
     grids_e = [OffloadBuffer.with_device(l.npts_local_total) for l in wl.layouts]
     hab_e = OffloadBuffer(wl.pab_len, pinned=True)
 
+    pin_pab = torch.from_numpy(pab_h.host).pin_memory() if world > 1 else None
+    pin_hab = torch.empty(wl.pab_len, dtype=torch.float64).pin_memory() if world > 1 else None
+
     def step_e2e():
-        tl.collocate(100, pab_e, grids_e)  # H2D pab, kernels, D2H grids
-        if world > 1:
-            exchange(grids_e)
-            for g in grids_e:
-                g.host[:] = g.device.cpu().numpy()[: g.host.size]
-        tl.integrate(False, pab_e if args.forces else None, grids_e, hab_e, forces, virial)  # H2D grids, D2H hab
+        if world == 1:
+            # host buffers through the public API: the library pipelines the P/H block
+            # copies against its coefficient kernels and copies the grids per level
+            tl.collocate(100, pab_e, grids_e)  # H2D pab, kernels, D2H grids
+            tl.integrate(False, pab_e if args.forces else None, grids_e, hab_e, forces, virial)  # H2D grids, D2H hab
+            return
+        # N > 1: the grids stay on the device between collocate, the exchange and
+        # integrate (device_buffer authoritative); this rank's P blocks come from
+        # pinned host memory and its H blocks go back to it every step
+        lib.set_device_resident(True)
+        pab.device.copy_(pin_pab, non_blocking=True)
+        tl.collocate(100, pab, grids)
+        exchange(grids)
+        tl.integrate(False, pab if args.forces else None, grids, hab, forces, virial)
+        if slab_levels is not None:
+            dist.all_reduce(hab.device)
+        pin_hab.copy_(hab.device[: wl.pab_len], non_blocking=True)
+        torch.cuda.synchronize()
 
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -386,8 +405,12 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_ms = float(dt.item()) / n_e2e * 1e3
-    h2d = 8 * wl.pab_len * (2 if args.forces else 1) + int(grid_bytes)
-    d2h = int(grid_bytes) + 8 * wl.pab_len
+    if world == 1:
+        h2d = 8 * wl.pab_len * (2 if args.forces else 1) + int(grid_bytes)
+        d2h = int(grid_bytes) + 8 * wl.pab_len
+    else:  # per rank: its P blocks in, its H blocks out (the grids never leave the device)
+        h2d = 8 * wl.pab_len
+        d2h = 8 * wl.pab_len
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
