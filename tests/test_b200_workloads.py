@@ -111,3 +111,33 @@ def test_adjointness_h2o256_full_size(b200):
     """BASELINE.json's headline configuration, all 1.25 M tasks."""
     defect, lin = _adjoint_defect(b200, build_h2o_workload("H2O-256"), 22)
     assert defect < 1e-12 and lin < 1e-12
+
+
+def test_h2o64_molopt_subset_against_reference_cpu_backend(b200, reference):
+    """BASELINE.json config 2's basis (DZVP-MOLOPT-SR: one l = 0..2 set per oxygen, so
+    every O-O product has lp = 4 -- the lp 3-4 kernel class carries the weight)."""
+    wl = build_h2o_workload("H2O-64", basis="DZVP-MOLOPT-SR-GTH", max_atoms=24)
+    assert wl.ntasks > 2000
+    pab = wl.random_pab(14)
+    ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab)
+    got = _run(b200, wl, pab)
+    for a, b in zip(got[0], ref[0]):
+        assert rel_diff(a, b) < 1e-10
+    assert rel_diff(got[1], ref[1]) < 1e-10
+    assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
+
+
+@pytest.mark.parametrize("func,tau", [(100, False), (200, True)])
+def test_nonortho_water_metagga_forces_virial(b200, reference, func, tau):
+    """BASELINE.json config 4: triclinic cell (general-cell path), density and
+    tau collocation, integrate with forces + virial (lp up to 9 with tau)."""
+    full = build_h2o_workload("H2O-64_nonortho", max_atoms=18)
+    assert not full.orthorhombic
+    wl = full.subset(np.arange(0, full.ntasks, 3))
+    pab = wl.random_pab(15)
+    ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab, forces=True, func=func, tau=tau)
+    got = _run(b200, wl, pab, forces=True, func=func, tau=tau)
+    for a, b in zip(got[0], ref[0]):
+        assert rel_diff(a, b) < 1e-10
+    assert rel_diff(got[1], ref[1]) < 1e-10
+    assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
