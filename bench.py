@@ -99,7 +99,7 @@ def split_blocks(wl, world, rank):
         load, r = heapq.heappop(heap)
         owner[b] = r
         heapq.heappush(heap, (load + bcost[b], r))
-    return wl.subset(owner[t["block_num_list"] - 1] == rank)
+    return wl.subset(owner[t["block_num_list"] - 1] == rank, compact_blocks=True)
 
 
 def run_reference(args):
@@ -249,11 +249,21 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # the NCCL version banner (NCCL_DEBUG=VERSION, also via /etc/nccl.conf) would precede
-        # the JSON line on stdout; an explicit NCCL_DEBUG=INFO etc. from the caller is kept
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL writes its version banner to stdout while the communicator is created; the
+        # contract is ONE JSON line on stdout, so fd 1 points at /dev/null meanwhile
+        sys.stdout.flush()
+        saved_fd, null_fd = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null_fd, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+            os.close(null_fd)
     lib = load_b200()
     lib.set_device(local_rank)
     lib.set_kernel_variant(args.variant)

@@ -320,11 +320,28 @@ class Workload:
             buf.host[:] = vals * np.repeat(decay, self.meta["block_sizes"])
         return buf
 
-    def subset(self, keep: np.ndarray) -> "Workload":
-        """Same system, only the tasks selected by the boolean/index array."""
+    def subset(self, keep: np.ndarray, compact_blocks: bool = False) -> "Workload":
+        """Same system, only the tasks selected by the boolean/index array.  With
+        `compact_blocks` the matrix blocks no kept task refers to are dropped and
+        the rest renumbered (what a rank owns in a distributed run: its P and H
+        block buffers hold its blocks only)."""
         tasks = {k: v[keep] for k, v in self.tasks.items()}
+        if not compact_blocks:
+            return Workload(self.orthorhombic, self.natoms, self.atom_positions, self.atom_kinds, self.basis_sets,
+                            self.layouts, self.block_offsets, tasks, self.pab_len, dict(self.meta))
+        sizes = np.diff(np.append(self.block_offsets.astype(np.int64), self.pab_len))
+        used = np.unique(tasks["block_num_list"] - 1)
+        new_num = np.full(self.nblocks, -1, dtype=np.int64)
+        new_num[used] = np.arange(used.size)
+        tasks["block_num_list"] = (new_num[tasks["block_num_list"] - 1] + 1).astype(np.int32)
+        new_sizes = sizes[used]
+        offsets = np.concatenate([[0], np.cumsum(new_sizes)[:-1]]).astype(np.int32) if used.size else np.zeros(0, np.int32)
+        meta = dict(self.meta)
+        if meta.get("block_decay") is not None:
+            meta["block_decay"] = np.asarray(meta["block_decay"])[used]
+        meta["block_sizes"] = new_sizes
         return Workload(self.orthorhombic, self.natoms, self.atom_positions, self.atom_kinds, self.basis_sets,
-                        self.layouts, self.block_offsets, tasks, self.pab_len, dict(self.meta))
+                        self.layouts, offsets, tasks, int(new_sizes.sum()), meta)
 
 
 def load_system(name: str):

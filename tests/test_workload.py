@@ -72,3 +72,34 @@ def test_nonortho_cell_is_triclinic():
     _, _, cell = W.load_system("H2O-64_nonortho")
     assert not np.allclose(cell, np.diag(np.diag(cell)))
     assert abs(np.linalg.norm(cell[0]) - 12.4138 * W.ANGSTROM) < 1e-9
+
+
+def test_compact_subset_is_the_same_task_list(oracle):
+    """Workload.subset(compact_blocks=True) -- a rank's share in a distributed run --
+    renumbers the blocks it keeps; with the matching P blocks the collocated
+    density is identical to the uncompacted subset's."""
+    from cp2k_b200.grid_api import OffloadBuffer
+    from cp2k_b200.workload import build_h2o_workload
+
+    w = build_h2o_workload("H2O-64", max_atoms=24)
+    keep = (w.tasks["block_num_list"] % 2) == 0
+    a, b = w.subset(keep), w.subset(keep, compact_blocks=True)
+    assert b.nblocks < a.nblocks and b.pab_len < a.pab_len and a.ntasks == b.ntasks
+    sizes = np.diff(np.append(w.block_offsets.astype(np.int64), w.pab_len))
+    used = np.unique(a.tasks["block_num_list"] - 1)
+    pa = a.random_pab(1)
+    pb = OffloadBuffer(b.pab_len)
+    pos = 0
+    for u in used:
+        pb.host[pos:pos + sizes[u]] = pa.host[w.block_offsets[u]:w.block_offsets[u] + sizes[u]]
+        pos += sizes[u]
+
+    def collocate(wl, p):
+        tl = wl.create(oracle)
+        g = wl.new_grids()
+        tl.collocate(100, p, g)
+        tl.free()
+        return np.concatenate([x.host for x in g])
+
+    ga, gb = collocate(a, pa), collocate(b, pb)
+    assert np.abs(ga).max() > 0 and np.array_equal(ga, gb)
