@@ -113,7 +113,7 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgrid_ref.so not built"}))
         return
     wl = build_h2o_workload(args.workload)
-    res = cpu_reference_timing(wl, args.steps, args.warmup, args.forces, budget_s=args.cpu_budget)
+    res = cpu_reference_timing(wl, args.steps, args.warmup, args.forces, budget_s=args.cpu_budget, virial=args.virial)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -133,7 +133,7 @@ METRIC = "grid collocate+integrate model FP64 GFLOP/s per SCF step (s/SCF-step =
 def bench_config(wl, args, extra=None):
     cfg = {"workload": f"{args.workload} GPW {wl.meta['basis']} cutoff 280 Ry rel_cutoff 30 Ry 4 levels "
                        f"{wl.meta['npts']}; step = collocate(GRID_FUNC_AB) + integrate"
-                       + ("+forces+virial" if args.forces else ""),
+                       + ("+forces" if args.forces else "") + ("+virial" if getattr(args, "virial", False) else ""),
            "ntasks": wl.ntasks, "nblocks": wl.nblocks, "natoms": wl.natoms,
            "l2": "per-step working set (task records + P/H blocks + grids > 0.5 GB) exceeds the 126 MB L2",
            "parallelism": (f"z-slab rs_grids over {args.gpus} GPU(s), NCCL halo sum/fill"
@@ -144,7 +144,7 @@ def bench_config(wl, args, extra=None):
     return cfg
 
 
-def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0):
+def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0, virial=False):
     """Times the unmodified reference CPU backend on a bounded sample of `wl`."""
     from cp2k_b200.grid_api import GRID_BACKEND_CPU, OffloadBuffer
     from oracle import pyref
@@ -160,7 +160,7 @@ def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0):
         grids = sample_wl.new_grids()
         hab = OffloadBuffer(sample_wl.pab_len)
         f = np.zeros((sample_wl.natoms, 3)) if forces else None
-        v = np.zeros((3, 3)) if forces else None
+        v = np.zeros((3, 3)) if virial else None
         times = []
         for i in range(nwarm + nsteps):
             t0 = time.perf_counter()
@@ -221,7 +221,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="H2O-256")
-    ap.add_argument("--forces", action="store_true")
+    ap.add_argument("--forces", action="store_true", help="integrate with forces (BASELINE config 3)")
+    ap.add_argument("--virial", action="store_true", help="... and the virial (implies --forces)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
@@ -230,6 +231,7 @@ def main():
                          "or z-slab rs_grids + NCCL halo sum/fill (cp2k_b200/rsgrid.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    args.forces = args.forces or args.virial
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -294,7 +296,7 @@ def main():
     grids = [OffloadBuffer.with_device(l.npts_local_total) for l in wl.layouts]
     hab = OffloadBuffer.with_device(wl.pab_len)
     forces = np.zeros((wl.natoms, 3)) if args.forces else None
-    virial = np.zeros((3, 3)) if args.forces else None
+    virial = np.zeros((3, 3)) if args.virial else None
 
     def exchange(gs):
         """The exchange step between collocate and integrate."""
@@ -427,7 +429,7 @@ def main():
         from oracle import pyref
 
         if pyref.have_reference():
-            r = cpu_reference_timing(wl_full, 2, 1, args.forces, budget_s=args.cpu_budget)
+            r = cpu_reference_timing(wl_full, 2, 1, args.forces, budget_s=args.cpu_budget, virial=args.virial)
             cpu_baseline = {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": "reference",
                             "sample": r["sample"], "ms_per_step_sample": r["ms_per_step"],
                             "ms_per_step_extrapolated": r["ms_per_step"] / r["sample_fraction"]}

@@ -49,7 +49,8 @@ namespace b200 {
 constexpr int kBX = 8, kBY = 8, kBZ = 16;     // block (warp footprint)
 constexpr int kTiledThreads = 128;            // 4 autonomous warps
 constexpr int kTiledWarps = kTiledThreads / 32;
-constexpr int kTiledMaxLp = 6;                // beyond: generic kernels
+constexpr int kTiledMaxLp = 6;                // max la_max + lb_max of a tiled task; beyond: generic kernels
+constexpr int kTiledMaxLpCall = 7;            // max lp including the call's l growth (forces + virial: +3)
 constexpr int kTiledMaxNb = 23;               // max cube half-width (sphere-table rows are 64 bytes)
 constexpr int kTiledMaxN = 30;                // max discretised radius index
 constexpr int kKPitch = 64;                   // sphere-table row pitch (bytes)
@@ -618,14 +619,33 @@ template <int LP> struct IntegrateReduce {
         for (int lx = 0; lx <= L2 - ly; lx++)
           part[q++] = X[lx] * w;
       }
-      int idx = WarpVecReduce<M>::run(part, lane);
-      if ((lane & (DupLanes<M>::value - 1)) == 0 && idx < M && part[0] != 0.0) {
+      // at most 32 values per transposing reduction (one result per lane)
+      constexpr int M1 = (M > 32) ? 32 : M, M2 = M - M1;
+      auto emit = [&](int idx, const double v) {
         int ly = 0;
         while (idx > L2 - ly) {
           idx -= L2 - ly + 1;
           ly++;
         }
-        atomicAdd(&gcoef[coset(idx, ly, LZ)], part[0]);
+        atomicAdd(&gcoef[coset(idx, ly, LZ)], v);
+      };
+      {
+        double head[M1];
+#pragma unroll
+        for (int i = 0; i < M1; i++)
+          head[i] = part[i];
+        const int idx = WarpVecReduce<M1>::run(head, lane);
+        if ((lane & (DupLanes<M1>::value - 1)) == 0 && idx < M1 && head[0] != 0.0)
+          emit(idx, head[0]);
+      }
+      if constexpr (M2 > 0) {
+        double rest[M2];
+#pragma unroll
+        for (int i = 0; i < M2; i++)
+          rest[i] = part[M1 + i];
+        const int idx = WarpVecReduce<M2>::run(rest, lane);
+        if ((lane & (DupLanes<M2>::value - 1)) == 0 && idx < M2 && rest[0] != 0.0)
+          emit(M1 + idx, rest[0]);
       }
       slice<LZ + 1>(X, Y0, Y1, S0, S1, gcoef, lane);
     }
@@ -971,7 +991,7 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
     if (A.nwork == 0)
       continue;
     const int lo = kClassLo[cls] + L.dl, hi = kClassHi[cls] + L.dl;
-    if (hi > kTiledMaxLp) {
+    if (hi > kTiledMaxLpCall) {
       leftover |= 1u << cls;
       continue;
     }
@@ -986,7 +1006,9 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
     else if (lo == 3) launch_tiled_class<COLLOCATE, 3, 4>(A, tl, s);
     else if (lo == 4 && hi == 6) launch_tiled_class<COLLOCATE, 4, 6>(A, tl, s);
     else if (lo == 4) launch_tiled_class<COLLOCATE, 4, 5>(A, tl, s);
+    else if (lo == 5 && hi == 7) launch_tiled_class<COLLOCATE, 5, 7>(A, tl, s);
     else if (lo == 5) launch_tiled_class<COLLOCATE, 5, 6>(A, tl, s);
+    else if (lo == 6 && hi == 7) launch_tiled_class<COLLOCATE, 6, 7>(A, tl, s);
     else leftover |= 1u << cls;
   }
   return leftover;
