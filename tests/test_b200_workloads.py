@@ -141,3 +141,16 @@ def test_nonortho_water_metagga_forces_virial(b200, reference, func, tau):
         assert rel_diff(a, b) < 1e-10
     assert rel_diff(got[1], ref[1]) < 1e-10
     assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
+
+
+def test_h2o64_full_against_reference_cpu_backend(b200, reference):
+    """The complete H2O-64 task list (362 k tasks: hundreds of pairs per grid block,
+    several work items per block) against the unmodified reference CPU backend."""
+    wl = build_h2o_workload("H2O-64")
+    pab = wl.random_pab(16)
+    ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab, forces=True)
+    got = _run(b200, wl, pab, forces=True)
+    for a, b in zip(got[0], ref[0]):
+        assert rel_diff(a, b) < 1e-10
+    assert rel_diff(got[1], ref[1]) < 1e-10
+    assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
