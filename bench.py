@@ -37,7 +37,7 @@ def load_traffic(workload, direction):
     (profiles/r01/traffic_r01b.json); None for workloads that were not captured."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic_r01b.json")))
-        return t[f"{direction}_bytes_per_call"] if t.get("workload") == workload else None
+        return t[f"{direction}_bytes_per_call"] if t.get("workload") == workload else None  # TZV2P capture
     except Exception:
         return None
 
@@ -112,7 +112,7 @@ def run_reference(args):
     if not pyref.have_reference():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgrid_ref.so not built"}))
         return
-    wl = build_h2o_workload(args.workload)
+    wl = build_h2o_workload(args.workload, basis=args.basis)
     res = cpu_reference_timing(wl, args.steps, args.warmup, args.forces, budget_s=args.cpu_budget, virial=args.virial)
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "GFLOP/s", "n_gpus": args.gpus,
@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="H2O-256")
+    ap.add_argument("--basis", default="TZV2P-GTH", choices=["TZV2P-GTH", "DZVP-MOLOPT-SR-GTH"],
+                    help="TZV2P-GTH as shipped in benchmarks/QS/H2O-N.inp; DZVP-MOLOPT-SR-GTH is BASELINE config 2's")
     ap.add_argument("--forces", action="store_true", help="integrate with forces (BASELINE config 3)")
     ap.add_argument("--virial", action="store_true", help="... and the virial (implies --forces)")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
@@ -270,7 +272,7 @@ def main():
     lib.set_device(local_rank)
     lib.set_kernel_variant(args.variant)
 
-    wl_full = build_h2o_workload(args.workload)
+    wl_full = build_h2o_workload(args.workload, basis=args.basis)
     slab_levels = None
     if args.decomp == "slab" and world > 1:
         from cp2k_b200 import rsgrid
@@ -368,7 +370,7 @@ def main():
         "bound": "fp64", "kernel": f"{dom} grid kernels (all levels of one call)",
         "achieved": achieved_tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
         "frac": achieved_tf / FP64_PEAK_TFLOPS,
-        "traffic": load_traffic(args.workload, dom) if world == 1 else None,
+        "traffic": load_traffic(args.workload, dom) if (world == 1 and args.basis == "TZV2P-GTH") else None,
         "peak_source": "measured DFMA loop, profiles/microbench (MEASURED_PEAKS.json has no FP64 entry)",
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (dom_ms * 1e-3) * 1e-9 if dom_ms else 0,
                 "peak_gbs": peaks.get("hbm_gbs"), "of": "fallback" if peaks.get("_fallback") else "measured"},
