@@ -340,8 +340,24 @@ class Workload:
         if meta.get("block_decay") is not None:
             meta["block_decay"] = np.asarray(meta["block_decay"])[used]
         meta["block_sizes"] = new_sizes
+        # where the kept blocks live in the parent's P/H buffers (for block_index_map)
+        meta["parent_block_ids"] = used
+        meta["parent_block_offsets"] = self.block_offsets.astype(np.int64)[used]
         return Workload(self.orthorhombic, self.natoms, self.atom_positions, self.atom_kinds, self.basis_sets,
                         self.layouts, offsets, tasks, int(new_sizes.sum()), meta)
+
+
+def block_index_map(sub: Workload) -> np.ndarray:
+    """For a `subset(compact_blocks=True)` workload: the index in the parent's
+    P/H block buffer of every element of the subset's (compacted) buffer, so that
+    `sub_buf[:] = parent_buf[idx]` gathers a rank's P blocks and
+    `parent_buf[idx] += sub_buf` scatters its H blocks back."""
+    sizes = np.asarray(sub.meta["block_sizes"], dtype=np.int64)
+    starts = np.asarray(sub.meta["parent_block_offsets"], dtype=np.int64)
+    if sizes.size == 0:
+        return np.zeros(0, dtype=np.int64)
+    local0 = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    return np.repeat(starts - local0, sizes) + np.arange(int(sizes.sum()), dtype=np.int64)
 
 
 def load_system(name: str):

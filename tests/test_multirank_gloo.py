@@ -44,15 +44,25 @@ def _worker(rank, world, port, mode, result_file):
         counts = torch.tensor([mine.ntasks], dtype=torch.int64)
         dist.all_reduce(counts)
         assert int(counts) == wl.ntasks  # a partition: nothing lost, nothing duplicated
+        # a rank's P/H buffers hold its own blocks only (compacted)
+        from cp2k_b200.workload import block_index_map
+        idx = block_index_map(mine)
+        sizes = torch.tensor([idx.size], dtype=torch.int64)
+        dist.all_reduce(sizes)
+        assert int(sizes) == wl.pab_len  # the blocks are partitioned too
+        my_pab = OffloadBuffer(mine.pab_len)
+        my_pab.host[:] = pab.host[idx]
         tl = mine.create(ora)
         grids = mine.new_grids()
-        tl.collocate(100, pab, grids)
+        tl.collocate(100, my_pab, grids)
         for g in grids:
             t = torch.from_numpy(g.host)
             dist.all_reduce(t)
         errs["grid"] = max(float(np.abs(g.host - f.host).max()) for g, f in zip(grids, full))
+        my_hab = OffloadBuffer(mine.pab_len)
+        tl.integrate(False, None, grids, my_hab)
         hab = OffloadBuffer(wl.pab_len)
-        tl.integrate(False, None, grids, hab)
+        hab.host[idx] = my_hab.host
         t = torch.from_numpy(hab.host)
         dist.all_reduce(t)
         errs["hab"] = float(np.abs(hab.host - hab_full.host).max())
