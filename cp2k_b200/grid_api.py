@@ -348,6 +348,127 @@ class B200Library(GridLibrary):
         L.grid_b200_set_timing.restype = None
         L.grid_b200_get_timings.argtypes = [_dptr, C.c_int]
         L.grid_b200_get_timings.restype = C.c_int
+        L.grid_b200_collocate_pgf_product.restype = None
+        L.grid_b200_collocate_pgf_product.argtypes = (
+            [C.c_bool, C.c_int, C.c_int] + [C.c_int] * 4 + [C.c_double] * 3 + [_dptr] * 4
+            + [_iptr] * 4 + [C.c_double] + [C.c_int] * 4 + [_dptr, _dptr])
+        L.grid_b200_integrate_pgf_product.restype = None
+        L.grid_b200_integrate_pgf_product.argtypes = (
+            [C.c_bool, C.c_bool, C.c_int] + [C.c_int] * 4 + [C.c_double] * 2 + [_dptr] * 4
+            + [_iptr] * 4 + [C.c_double] + [C.c_int] * 4 + [_dptr] * 8)
+        _pp = C.POINTER(_dptr)
+        L.grid_b200_collocate_pgf_products.restype = None
+        L.grid_b200_collocate_pgf_products.argtypes = (
+            [C.c_int, C.c_bool, C.c_int] + [_iptr] * 5 + [_dptr] * 6 + [_iptr] * 4 + [_pp]
+            + [_dptr] * 2 + [_iptr] * 4 + [_dptr])
+        L.grid_b200_integrate_pgf_products.restype = None
+        L.grid_b200_integrate_pgf_products.argtypes = (
+            [C.c_int, C.c_bool, C.c_bool] + [_iptr] * 5 + [_dptr] * 5 + [_iptr] * 4
+            + [_dptr] * 2 + [_iptr] * 4 + [_dptr, _pp, _pp, _dptr])
+
+    # -- ad-hoc Gaussian products: module grid_api's collocate_pgf_product /
+    # -- integrate_pgf_product (src/grid/grid_api.F:110-236, 267-490)
+    def collocate_pgf_product(self, *, orthorhombic, border_mask, func, la_max, la_min, lb_max, lb_min,
+                              zeta, zetb, rscale, layout: "GridLayout", ra, rab, radius, o1, o2, pab,
+                              grid: np.ndarray) -> None:
+        """ADDS one Gaussian product to ``grid`` (float64, npts_local points)."""
+        pab = _f64(pab)
+        n2, n1 = pab.shape
+        assert grid.dtype == np.float64 and grid.flags.c_contiguous
+        ra, rab = _f64(ra), _f64(rab)
+        a = [_f64(layout.dh).reshape(-1), _f64(layout.dh_inv).reshape(-1)]
+        n = [_i32(layout.npts_global), _i32(layout.npts_local), _i32(layout.shift_local),
+             _i32(layout.border_width)]
+        self.lib.grid_b200_collocate_pgf_product(
+            bool(orthorhombic), int(border_mask), int(func), int(la_max), int(la_min), int(lb_max),
+            int(lb_min), float(zeta), float(zetb), float(rscale), _dp(a[0]), _dp(a[1]), _dp(ra), _dp(rab),
+            _ip(n[0]), _ip(n[1]), _ip(n[2]), _ip(n[3]), float(radius), int(o1), int(o2), int(n1), int(n2),
+            _dp(pab.reshape(-1)), _dp(grid.reshape(-1)))
+
+    def integrate_pgf_product(self, *, orthorhombic, compute_tau, border_mask, la_max, la_min, lb_max,
+                              lb_min, zeta, zetb, layout: "GridLayout", ra, rab, radius, o1, o2,
+                              grid: np.ndarray, hab: np.ndarray, pab=None,
+                              forces: Optional[np.ndarray] = None) -> None:
+        """ADDS the product's integrals to ``hab[n2][n1]`` (and its force
+        contributions to ``forces[2][3]`` when given; needs ``pab``)."""
+        assert hab.dtype == np.float64 and hab.flags.c_contiguous and hab.ndim == 2
+        n2, n1 = hab.shape
+        ra, rab, grid = _f64(ra), _f64(rab), _f64(grid)
+        pabc = _f64(pab).reshape(-1) if pab is not None else None
+        if forces is not None:
+            assert forces.dtype == np.float64 and forces.flags.c_contiguous and forces.size == 6
+            assert pabc is not None and pabc.size == n1 * n2
+        a = [_f64(layout.dh).reshape(-1), _f64(layout.dh_inv).reshape(-1)]
+        n = [_i32(layout.npts_global), _i32(layout.npts_local), _i32(layout.shift_local),
+             _i32(layout.border_width)]
+        null = C.cast(None, _dptr)
+        self.lib.grid_b200_integrate_pgf_product(
+            bool(orthorhombic), bool(compute_tau), int(border_mask), int(la_max), int(la_min), int(lb_max),
+            int(lb_min), float(zeta), float(zetb), _dp(a[0]), _dp(a[1]), _dp(ra), _dp(rab), _ip(n[0]),
+            _ip(n[1]), _ip(n[2]), _ip(n[3]), float(radius), int(o1), int(o2), int(n1), int(n2),
+            _dp(grid.reshape(-1)), _dp(hab.reshape(-1)), _dp(pabc) if pabc is not None else null,
+            _dp(forces.reshape(-1)) if forces is not None else null, null, null, null, null)
+
+    @staticmethod
+    def _ptr_array(mats):
+        arr = (_dptr * len(mats))()
+        for i, m in enumerate(mats):
+            arr[i] = _dp(m.reshape(-1))
+        return arr
+
+    def collocate_pgf_products(self, *, orthorhombic, func, border_mask, la_max, la_min, lb_max, lb_min,
+                               zeta, zetb, rscale, layout: "GridLayout", ra, rab, radius, o1, o2, pab,
+                               grid: np.ndarray) -> None:
+        """Batched form: n products for one grid in ONE device pass.  Per-product
+        arguments are sequences of length n; ``pab`` is a list of [n2][n1] arrays."""
+        pabs = [_f64(m) for m in pab]
+        nprod = len(pabs)
+        n1 = _i32([m.shape[1] for m in pabs])
+        n2 = _i32([m.shape[0] for m in pabs])
+        iv = [_i32(np.broadcast_to(v, (nprod,))) for v in (border_mask, la_max, la_min, lb_max, lb_min)]
+        dv = [_f64(np.broadcast_to(v, (nprod,))) for v in (zeta, zetb, rscale)]
+        ra, rab = _f64(ra).reshape(nprod, 3), _f64(rab).reshape(nprod, 3)
+        rad = _f64(np.broadcast_to(radius, (nprod,)))
+        o1, o2 = _i32(np.broadcast_to(o1, (nprod,))), _i32(np.broadcast_to(o2, (nprod,)))
+        assert grid.dtype == np.float64 and grid.flags.c_contiguous
+        a = [_f64(layout.dh).reshape(-1), _f64(layout.dh_inv).reshape(-1)]
+        n = [_i32(layout.npts_global), _i32(layout.npts_local), _i32(layout.shift_local),
+             _i32(layout.border_width)]
+        self.lib.grid_b200_collocate_pgf_products(
+            nprod, bool(orthorhombic), int(func), *[_ip(v) for v in iv], *[_dp(v) for v in dv],
+            _dp(ra.reshape(-1)), _dp(rab.reshape(-1)), _dp(rad), _ip(o1), _ip(o2), _ip(n1), _ip(n2),
+            self._ptr_array(pabs), _dp(a[0]), _dp(a[1]), _ip(n[0]), _ip(n[1]), _ip(n[2]), _ip(n[3]),
+            _dp(grid.reshape(-1)))
+
+    def integrate_pgf_products(self, *, orthorhombic, compute_tau, border_mask, la_max, la_min, lb_max,
+                               lb_min, zeta, zetb, layout: "GridLayout", ra, rab, radius, o1, o2,
+                               grid: np.ndarray, hab, pab=None, forces: Optional[np.ndarray] = None) -> None:
+        """Batched form of integrate_pgf_product; ``hab`` is a list of float64
+        [n2][n1] arrays (accumulated in place), ``forces`` is [n][2][3]."""
+        nprod = len(hab)
+        for m in hab:
+            assert m.dtype == np.float64 and m.flags.c_contiguous and m.ndim == 2
+        n1 = _i32([m.shape[1] for m in hab])
+        n2 = _i32([m.shape[0] for m in hab])
+        iv = [_i32(np.broadcast_to(v, (nprod,))) for v in (border_mask, la_max, la_min, lb_max, lb_min)]
+        dv = [_f64(np.broadcast_to(v, (nprod,))) for v in (zeta, zetb)]
+        ra, rab = _f64(ra).reshape(nprod, 3), _f64(rab).reshape(nprod, 3)
+        rad = _f64(np.broadcast_to(radius, (nprod,)))
+        o1, o2 = _i32(np.broadcast_to(o1, (nprod,))), _i32(np.broadcast_to(o2, (nprod,)))
+        grid = _f64(grid)
+        pabs = [_f64(m) for m in pab] if pab is not None else None
+        if forces is not None:
+            assert forces.dtype == np.float64 and forces.flags.c_contiguous and forces.size == 6 * nprod
+            assert pabs is not None
+        a = [_f64(layout.dh).reshape(-1), _f64(layout.dh_inv).reshape(-1)]
+        n = [_i32(layout.npts_global), _i32(layout.npts_local), _i32(layout.shift_local),
+             _i32(layout.border_width)]
+        self.lib.grid_b200_integrate_pgf_products(
+            nprod, bool(orthorhombic), bool(compute_tau), *[_ip(v) for v in iv], *[_dp(v) for v in dv],
+            _dp(ra.reshape(-1)), _dp(rab.reshape(-1)), _dp(rad), _ip(o1), _ip(o2), _ip(n1), _ip(n2),
+            _dp(a[0]), _dp(a[1]), _ip(n[0]), _ip(n[1]), _ip(n[2]), _ip(n[3]), _dp(grid.reshape(-1)),
+            self._ptr_array(hab), self._ptr_array(pabs) if pabs is not None else C.cast(None, C.POINTER(_dptr)),
+            _dp(forces.reshape(-1)) if forces is not None else C.cast(None, _dptr))
 
     def set_device(self, device: int) -> None:
         self.lib.grid_b200_set_device(int(device))

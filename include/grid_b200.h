@@ -90,6 +90,70 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *task_list,
                                    grid_b200_buffer *hab_blocks, double *forces,
                                    double *virial);
 
+/* ---- ad-hoc Gaussian products ---------------------
+ *
+ * grid_b200_collocate_pgf_product replaces grid_cpu_collocate_pgf_product
+ * (src/grid/cpu/grid_cpu_collocate.h:49-58), the function behind module
+ * grid_api's collocate_pgf_product (src/grid/grid_api.F:110-236), with the
+ * same arguments in the same order (dh/dh_inv are [3][3], ra/rab [3], the
+ * npts/shift/border arrays [3], pab is [n2][n1]); it ADDS the product
+ * rscale * sum_ab pab[o2+b][o1+a] g_a g_b (after `func`'s transformation) to
+ * `grid` (npts_local doubles, host memory).
+ * grid_b200_integrate_pgf_product replaces grid_cpu_integrate_pgf_product
+ * (src/grid/cpu/grid_cpu_integrate.h:51-62; grid_api.F:267-490): ADDS the
+ * integrals to hab[o2+b][o1+a] and, if `forces` ([2][3]) is non-NULL, the
+ * force contributions (needs pab).  `virials`, `hdab`, `hadb` and `a_hdab`
+ * must be NULL: the call aborts otherwise (the summed virial is available
+ * from grid_b200_integrate_task_list).
+ *
+ * The *_pgf_products forms take n products for ONE grid in one call (per-
+ * product arrays of length n; ra/rab are [n][3]; pab/hab are arrays of n
+ * pointers to [n2[p]][n1[p]] matrices; forces is [n][2][3]) -- one task-list
+ * build, one upload and one kernel pass for the whole batch, which is how
+ * callers that loop over products (src/qs_collocate_density.F:1808-2014)
+ * should use a GPU. */
+void grid_b200_collocate_pgf_product(
+    const bool orthorhombic, const int border_mask, const int func,
+    const int la_max, const int la_min, const int lb_max, const int lb_min,
+    const double zeta, const double zetb, const double rscale,
+    const double *dh, const double *dh_inv, const double *ra,
+    const double *rab, const int *npts_global, const int *npts_local,
+    const int *shift_local, const int *border_width, const double radius,
+    const int o1, const int o2, const int n1, const int n2, const double *pab,
+    double *grid);
+
+void grid_b200_integrate_pgf_product(
+    const bool orthorhombic, const bool compute_tau, const int border_mask,
+    const int la_max, const int la_min, const int lb_max, const int lb_min,
+    const double zeta, const double zetb, const double *dh,
+    const double *dh_inv, const double *ra, const double *rab,
+    const int *npts_global, const int *npts_local, const int *shift_local,
+    const int *border_width, const double radius, const int o1, const int o2,
+    const int n1, const int n2, const double *grid, double *hab,
+    const double *pab, double *forces, double *virials, double *hdab,
+    double *hadb, double *a_hdab);
+
+void grid_b200_collocate_pgf_products(
+    const int nproducts, const bool orthorhombic, const int func,
+    const int *border_mask, const int *la_max, const int *la_min,
+    const int *lb_max, const int *lb_min, const double *zeta,
+    const double *zetb, const double *rscale, const double *ra,
+    const double *rab, const double *radius, const int *o1, const int *o2,
+    const int *n1, const int *n2, const double *const *pab, const double *dh,
+    const double *dh_inv, const int *npts_global, const int *npts_local,
+    const int *shift_local, const int *border_width, double *grid);
+
+void grid_b200_integrate_pgf_products(
+    const int nproducts, const bool orthorhombic, const bool compute_tau,
+    const int *border_mask, const int *la_max, const int *la_min,
+    const int *lb_max, const int *lb_min, const double *zeta,
+    const double *zetb, const double *ra, const double *rab,
+    const double *radius, const int *o1, const int *o2, const int *n1,
+    const int *n2, const double *dh, const double *dh_inv,
+    const int *npts_global, const int *npts_local, const int *shift_local,
+    const int *border_width, const double *grid, double *const *hab,
+    const double *const *pab, double *forces);
+
 /* ---- backend controls (no counterpart in the reference) ------------------ */
 
 /* Device selection follows offload_get_chosen_device()
