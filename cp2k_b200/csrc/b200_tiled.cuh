@@ -74,13 +74,14 @@ struct TTask {            // static per-task data of the tiled path
   int n;                  // discretised radius index
   int lp0;                // la_max + lb_max
   int task;               // index into the TaskDev array
+  unsigned epack;         // exp-table locator: (first double of the task's rows / 2) << 5 | nbq
 };
 
 struct alignas(16) TPair {  // 16 bytes, read as one uint4 (warp-uniform)
   unsigned q;             // ttask index
   unsigned kbase;         // sphere-table index of block column (0,0)
   unsigned opk;           // byte 0..2: cube centre relative to the block origin (signed), byte 3: wlo | whi << 4
-  unsigned pad;
+  unsigned epack;         // the task's exp-table locator (TTask::epack)
 };
 
 struct alignas(16) TWork {  // 32 bytes
@@ -291,7 +292,7 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
                 P.kbase = (unsigned)(H.offset + (X.nb[1] + kKPad - oy) * kKPitch + (X.nb[0] + kKPad - ox));
                 P.opk = ((unsigned)ox & 0xffu) | (((unsigned)oy & 0xffu) << 8) | (((unsigned)oz & 0xffu) << 16) |
                         ((unsigned)wlo << 24) | ((unsigned)whi << 28);
-                P.pad = 0;
+                P.epack = X.epack;
                 A.pairs[pos] = P;
                 A.keys[pos] = ((unsigned long long)bucket << A.qbits) | (unsigned long long)q;
               }
@@ -303,31 +304,37 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
   }
 }
 
-// exp tables, one row of P doubles per (task, axis):
-//   row[0] = roffset,  row[1 + t] = exp(-zetp (g*h - roff)^2) with g = t - max_nb - 1
+// exp tables.  A task's three rows (x, y, z) have Pq = 2 nbq + 5 doubles each, with
+// nbq = the task's largest cube half-width, and start at double 2 * (epack >> 5):
+//   row[0] = roffset,  row[1 + t] = exp(-zetp (g*h - roff)^2) with g = t - nbq - 1
 // for g inside the cube [-nb, nb+1] and 0 outside (both ends are zero guards).
-__global__ void etab_kernel(const TTask *ttasks, const TaskDev *tasks, const int nttasks, const int P,
-                            const int max_nb, const double hx, const double hy, const double hz,
-                            double *etab) {
+// Rows are sized per task (not per level): the table is the kernels' dominant
+// DRAM stream and its working set decides the L2 hit rate.
+__host__ __device__ inline int etab_pitch(const int nbq) { return 2 * nbq + 5; }
+__global__ void etab_kernel(const TTask *ttasks, const TaskDev *tasks, const int nttasks, const int Pmax,
+                            const double hx, const double hy, const double hz, double *etab) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)nttasks * 3 * P;
+  const size_t total = (size_t)nttasks * 3 * Pmax;
   if (idx >= total)
     return;
-  const int e = (int)(idx % P), d = (int)((idx / P) % 3);
-  const int q = (int)(idx / ((size_t)3 * P));
+  const int e = (int)(idx % Pmax), d = (int)((idx / Pmax) % 3);
+  const int q = (int)(idx / ((size_t)3 * Pmax));
   const TTask &X = ttasks[q];
+  const int nbq = (int)(X.epack & 31u), Pq = etab_pitch(nbq);
+  if (e >= Pq)
+    return;
   double v = 0.0;
   if (e == 0) {
     v = X.roff[d];
   } else {
-    const int g = e - 1 - (max_nb + 1);
+    const int g = e - 1 - (nbq + 1);
     if (g >= -X.nb[d] && g <= X.nb[d] + 1) {
       const double h = (d == 0) ? hx : ((d == 1) ? hy : hz);
       const double x = g * h - X.roff[d];
       v = exp(-tasks[X.task].zetp * x * x);
     }
   }
-  etab[idx] = v;
+  etab[(size_t)2 * (X.epack >> 5) + (size_t)d * Pq + e] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -400,7 +407,15 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
     B200_ASSERT(heads[X.n].offset >= 0 && X.nb[0] == heads[X.n].nbx && X.nb[1] == heads[X.n].nby &&
                     X.nb[2] == heads[X.n].nbz,
                 "cube bounds disagree with the sphere table");
-  tl.P = 2 * max_nb + 5;  // roff + e(-max_nb-1 .. max_nb+2)
+  // exp-table locators (after the class sort: q is final)
+  size_t etab_len = 0;
+  for (TTask &X : tt) {
+    const int nbq = std::max(X.nb[0], std::max(X.nb[1], X.nb[2]));
+    B200_ASSERT(nbq < 32 && etab_len / 2 < ((size_t)1 << 27), "exp table too large for its 27-bit locator");
+    X.epack = (unsigned)((etab_len / 2) << 5) | (unsigned)nbq;
+    etab_len += (size_t)(3 * etab_pitch(nbq) + 1) / 2 * 2;  // 16-byte granularity
+  }
+  tl.P = etab_pitch(max_nb);
 
   auto up = [&](auto **dst, const auto &vec) {
     using T = typename std::remove_reference<decltype(vec)>::type::value_type;
@@ -415,10 +430,13 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   up(&tl.d_zmask, zmask);
 
   // exp tables
-  const size_t etab_len = (size_t)tt.size() * 3 * tl.P;
-  B200_CHECK(cudaMalloc((void **)&tl.d_etab, etab_len * sizeof(double)));
-  etab_kernel<<<(unsigned)((etab_len + 255) / 256), 256, 0, s>>>(tl.d_ttasks, d_tasks, (int)tt.size(), tl.P,
-                                                                max_nb, h[0], h[1], h[2], tl.d_etab);
+  B200_CHECK(cudaMalloc((void **)&tl.d_etab, std::max<size_t>(etab_len, 2) * sizeof(double)));
+  B200_CHECK(cudaMemsetAsync(tl.d_etab, 0, std::max<size_t>(etab_len, 2) * sizeof(double), s));  // row padding
+  {
+    const size_t nthreads = (size_t)tt.size() * 3 * tl.P;
+    etab_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, s>>>(tl.d_ttasks, d_tasks, (int)tt.size(), tl.P,
+                                                                  h[0], h[1], h[2], tl.d_etab);
+  }
   B200_CHECK(cudaGetLastError());
   count_launch();
 
@@ -697,14 +715,14 @@ __device__ __forceinline__ int sext_byte(const unsigned v, const unsigned pos) {
 // Per-lane constants of the pair loops.
 struct LaneCtx {
   const uint4 *__restrict__ pairs;
-  const double *__restrict__ etab_axis;  // etab + my_axis * P
+  const double *__restrict__ etab;       // exp tables of the level
   const double *__restrict__ coef_lane;  // coef + coef_base + lane
   double *__restrict__ coef0;            // coef + coef_base
   const unsigned char *__restrict__ ktab_lane;  // ktab + lj * kKPitch + li
   const unsigned short *__restrict__ s_zm;      // shared copy of the plane-mask table (biased)
   double *__restrict__ ws;               // this warp's scratch (two stages)
   double my_h;
-  int row3, gbias, ge_max, my_t;
+  int my_axis, my_t;
   unsigned sel;                          // bit position of my axis' byte in opk
   int tt_first, coef_stride;
   int lane, li, lj;
@@ -734,8 +752,9 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
 #define B200_FETCH(R)                                                          \
   {                                                                            \
     o_n = sext_byte(R.z, c.sel);                                               \
-    const int ge_ = min(max(c.gbias - o_n, 0), c.ge_max);                      \
-    const double *row_ = c.etab_axis + (size_t)R.x * (unsigned)c.row3;         \
+    const int nbq_ = (int)(R.w & 31u), pq_ = 2 * nbq_ + 5;                     \
+    const int ge_ = min(max(c.my_t + nbq_ + 1 - o_n, 0), pq_ - 2);             \
+    const double *row_ = c.etab + 2 * (size_t)(R.w >> 5) + c.my_axis * pq_;    \
     roff_n = __ldg(row_);                                                      \
     e_n = __ldg(row_ + 1 + ge_);                                               \
     if (COLLOCATE) {                                                           \
@@ -884,10 +903,8 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kern
   c.my_t = (lane < 8) ? lane : ((lane < 16) ? lane - 8 : lane - 16);
   c.my_h = (my_axis == 0) ? A.hx : ((my_axis == 1) ? A.hy : A.hz);
   c.sel = 8u * my_axis;
-  c.row3 = 3 * A.P;
-  c.etab_axis = A.etab + my_axis * A.P;
-  c.gbias = c.my_t + A.max_nb + 1;  // etab entry index = gbias - o
-  c.ge_max = A.P - 2;
+  c.my_axis = my_axis;
+  c.etab = A.etab;
   c.coef0 = A.coef + A.coef_base;
   c.coef_lane = c.coef0 + lane;
   c.tt_first = A.tt_first, c.coef_stride = A.coef_stride;

@@ -113,6 +113,25 @@ def test_adjointness_h2o256_full_size(b200):
     assert defect < 1e-12 and lin < 1e-12
 
 
+def test_adjointness_h2o1024_full_size(b200):
+    """BASELINE.json config 5: H2O-1024, 5.0 M tasks on four levels (315/189/105/63)^3."""
+    defect, lin = _adjoint_defect(b200, build_h2o_workload("H2O-1024"), 23)
+    assert defect < 1e-12 and lin < 1e-12
+
+
+def test_h2o256_full_against_reference_cpu_backend(b200, reference):
+    """The headline configuration itself (H2O-256, 1.25 M tasks, with forces): every
+    grid value and every H element against the unmodified reference CPU backend."""
+    wl = build_h2o_workload("H2O-256")
+    pab = wl.random_pab(17)
+    ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab, forces=True)
+    got = _run(b200, wl, pab, forces=True)
+    for a, b in zip(got[0], ref[0]):
+        assert rel_diff(a, b) < 1e-10
+    assert rel_diff(got[1], ref[1]) < 1e-10
+    assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
+
+
 def test_h2o64_molopt_subset_against_reference_cpu_backend(b200, reference):
     """BASELINE.json config 2's basis (DZVP-MOLOPT-SR: one l = 0..2 set per oxygen, so
     every O-O product has lp = 4 -- the lp 3-4 kernel class carries the weight)."""
