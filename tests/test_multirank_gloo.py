@@ -70,6 +70,8 @@ def _worker(rank, world, port, mode, result_file):
     else:
         levels = rsgrid.make_slab_levels(wl, world)
         assert any(l.distributed for l in levels)
+        if world > 2:  # the case this test is for: halo wider than a slab
+            assert any(l.distributed and l.border > l.owned[0][1] - l.owned[0][0] for l in levels)
         mine = rsgrid.local_workload(wl, levels, rank, world)
         counts = torch.tensor([mine.ntasks], dtype=torch.int64)
         dist.all_reduce(counts)
@@ -106,11 +108,13 @@ def _worker(rank, world, port, mode, result_file):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["replicated", "slab"])
-def test_two_ranks(mode, tmp_path):
-    port = 29500 + (os.getpid() % 400) + (0 if mode == "replicated" else 401)
+@pytest.mark.parametrize("mode,world", [("replicated", 2), ("slab", 2), ("slab", 6)])
+def test_ranks(mode, world, tmp_path):
+    """world 6 on a 72-plane level: slabs of 12 planes are thinner than the halo,
+    so the halo sum / fill reaches beyond the nearest neighbour."""
+    port = 29500 + (os.getpid() % 400) + (0 if mode == "replicated" else 401 * world // 2)
     out = str(tmp_path / "res.npy")
-    mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, mode, out), nprocs=world, join=True)
     grid_err, hab_err = np.load(out)
     assert grid_err < 1e-11
     assert hab_err < 1e-10
