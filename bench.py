@@ -33,13 +33,19 @@ FP64_PEAK_TFLOPS = 36.1  # measured on this pool's B200 (profiles/microbench/mb.
 
 
 def load_traffic(workload, direction):
-    """DRAM bytes per call of the grid kernels from the committed ncu capture
-    (profiles/r01/traffic_r01b.json); None for workloads that were not captured."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01", "traffic_r01b.json")))
-        return t[f"{direction}_bytes_per_call"] if t.get("workload") == workload else None  # TZV2P capture
-    except Exception:
-        return None
+    """DRAM bytes per call of the grid kernels from the newest committed ncu capture
+    (profiles/*/traffic_*.json, written by tools/traffic_from_ncu.py); None for
+    workloads that were not captured."""
+    import glob
+
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*", "traffic_*.json")), reverse=True):
+        try:
+            t = json.load(open(path))
+            if t.get("workload") == workload:  # TZV2P capture
+                return t[f"{direction}_bytes_per_call"]
+        except Exception:
+            continue
+    return None
 
 
 def load_peaks():
@@ -59,7 +65,29 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
 
+    def _nvml_loop(self):
+        """NVML polled every 10 ms (an nvidia-smi process per sample takes longer than
+        a whole step); same fields and the same reason names as the nvidia-smi query."""
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        vmax = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [0x8, 0x40, 0x20, 0x4]  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self._stop_evt.is_set():
+            r = int(get_reasons(h))
+            self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(vmax)]
+                                + ["Active" if r & b else "Not Active" for b in bits])
+            self._stop_evt.wait(0.01)
+
     def run(self):
+        try:
+            self._nvml_loop()
+            return
+        except Exception:
+            pass
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",

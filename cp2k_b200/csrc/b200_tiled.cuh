@@ -60,6 +60,7 @@ constexpr int kZmBias = 24;
 constexpr int kZmRows = kTiledMaxNb + 2;
 constexpr int kLpBuckets = kTiledMaxLp + 1;
 constexpr int kItemPairs = 512;               // pairs per work item (upper bound)
+constexpr int kPairPad = 9;                   // records after the last pair (copies of it)
 // lp classes (by lp0 = la_max + lb_max): separate kernel instantiations keep the
 // code of each kernel small (instruction cache!) and the registers low
 constexpr int kNumClasses = 3;
@@ -74,13 +75,13 @@ struct TTask {            // static per-task data of the tiled path
   int n;                  // discretised radius index
   int lp0;                // la_max + lb_max
   int task;               // index into the TaskDev array
-  unsigned epack;         // exp-table locator: (first double of the task's rows / 2) << 5 | nbq
+  unsigned epack;         // exp-table locator: (first double of the task's block / 4) << 5 | nbq
 };
 
 struct alignas(16) TPair {  // 16 bytes, read as one uint4 (warp-uniform)
   unsigned q;             // ttask index
   unsigned kbase;         // sphere-table index of block column (0,0)
-  unsigned opk;           // byte 0..2: cube centre relative to the block origin (signed), byte 3: wlo | whi << 4
+  unsigned opk;           // bytes 0, 1, 3: cube centre (x, y, z) relative to the block origin (signed); byte 2: wlo | whi << 4
   unsigned epack;         // the task's exp-table locator (TTask::epack)
 };
 
@@ -290,8 +291,8 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
                 TPair P;
                 P.q = (unsigned)q;
                 P.kbase = (unsigned)(H.offset + (X.nb[1] + kKPad - oy) * kKPitch + (X.nb[0] + kKPad - ox));
-                P.opk = ((unsigned)ox & 0xffu) | (((unsigned)oy & 0xffu) << 8) | (((unsigned)oz & 0xffu) << 16) |
-                        ((unsigned)wlo << 24) | ((unsigned)whi << 28);
+                P.opk = ((unsigned)ox & 0xffu) | (((unsigned)oy & 0xffu) << 8) | (((unsigned)oz & 0xffu) << 24) |
+                        ((unsigned)wlo << 16) | ((unsigned)whi << 20);
                 P.epack = X.epack;
                 A.pairs[pos] = P;
                 A.keys[pos] = ((unsigned long long)bucket << A.qbits) | (unsigned long long)q;
@@ -304,37 +305,41 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
   }
 }
 
-// exp tables.  A task's three rows (x, y, z) have Pq = 2 nbq + 5 doubles each, with
-// nbq = the task's largest cube half-width, and start at double 2 * (epack >> 5):
-//   row[0] = roffset,  row[1 + t] = exp(-zetp (g*h - roff)^2) with g = t - nbq - 1
-// for g inside the cube [-nb, nb+1] and 0 outside (both ends are zero guards).
-// Rows are sized per task (not per level): the table is the kernels' dominant
-// DRAM stream and its working set decides the L2 hit rate.
-__host__ __device__ inline int etab_pitch(const int nbq) { return 2 * nbq + 5; }
+// exp tables.  A task's block starts at double 4 * (epack >> 5) and holds, with
+// nbq = the task's largest cube half-width (epack & 31):
+//   [roff_x, roff_y, roff_z, 0]
+//   x row: exp(-zetp (g*h - roff)^2) for g = -nbq-7  .. nbq+8    (2 nbq + 16 entries)
+//   y row: likewise                                               (2 nbq + 16 entries)
+//   z row:                           for g = -nbq-15 .. nbq+16   (2 nbq + 32 entries)
+// with zeros outside the cube [-nb, nb+1].  The rows cover every offset a block that
+// overlaps the cube can ask for (block extents 8, 8, 16), so the kernels index them
+// without clamping.  Blocks are sized per task (not per level).
+__host__ __device__ inline int etab_doubles(const int nbq) { return (6 * nbq + 68 + 3) / 4 * 4; }
 __global__ void etab_kernel(const TTask *ttasks, const TaskDev *tasks, const int nttasks, const int Pmax,
                             const double hx, const double hy, const double hz, double *etab) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t total = (size_t)nttasks * 3 * Pmax;
-  if (idx >= total)
+  if (idx >= (size_t)nttasks * Pmax)
     return;
-  const int e = (int)(idx % Pmax), d = (int)((idx / Pmax) % 3);
-  const int q = (int)(idx / ((size_t)3 * Pmax));
+  const int e = (int)(idx % Pmax), q = (int)(idx / Pmax);
   const TTask &X = ttasks[q];
-  const int nbq = (int)(X.epack & 31u), Pq = etab_pitch(nbq);
-  if (e >= Pq)
+  const int nbq = (int)(X.epack & 31u), rx = 2 * nbq + 16;
+  if (e >= etab_doubles(nbq))
     return;
   double v = 0.0;
-  if (e == 0) {
-    v = X.roff[d];
-  } else {
-    const int g = e - 1 - (nbq + 1);
+  if (e < 4) {
+    if (e < 3)
+      v = X.roff[e];
+  } else if (e < 4 + 2 * rx + (2 * nbq + 32)) {
+    const int r = e - 4;
+    const int d = (r < rx) ? 0 : ((r < 2 * rx) ? 1 : 2);
+    const int g = r - d * rx - nbq - ((d == 2) ? 15 : 7);
     if (g >= -X.nb[d] && g <= X.nb[d] + 1) {
       const double h = (d == 0) ? hx : ((d == 1) ? hy : hz);
       const double x = g * h - X.roff[d];
       v = exp(-tasks[X.task].zetp * x * x);
     }
   }
-  etab[(size_t)2 * (X.epack >> 5) + (size_t)d * Pq + e] = v;
+  etab[(size_t)4 * (X.epack >> 5) + e] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -411,11 +416,11 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   size_t etab_len = 0;
   for (TTask &X : tt) {
     const int nbq = std::max(X.nb[0], std::max(X.nb[1], X.nb[2]));
-    B200_ASSERT(nbq < 32 && etab_len / 2 < ((size_t)1 << 27), "exp table too large for its 27-bit locator");
-    X.epack = (unsigned)((etab_len / 2) << 5) | (unsigned)nbq;
-    etab_len += (size_t)(3 * etab_pitch(nbq) + 1) / 2 * 2;  // 16-byte granularity
+    B200_ASSERT(nbq < 32 && etab_len / 4 < ((size_t)1 << 27), "exp table too large for its 27-bit locator");
+    X.epack = (unsigned)((etab_len / 4) << 5) | (unsigned)nbq;
+    etab_len += (size_t)etab_doubles(nbq);
   }
-  tl.P = etab_pitch(max_nb);
+  tl.P = etab_doubles(max_nb);
 
   auto up = [&](auto **dst, const auto &vec) {
     using T = typename std::remove_reference<decltype(vec)>::type::value_type;
@@ -430,10 +435,9 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   up(&tl.d_zmask, zmask);
 
   // exp tables
-  B200_CHECK(cudaMalloc((void **)&tl.d_etab, std::max<size_t>(etab_len, 2) * sizeof(double)));
-  B200_CHECK(cudaMemsetAsync(tl.d_etab, 0, std::max<size_t>(etab_len, 2) * sizeof(double), s));  // row padding
+  B200_CHECK(cudaMalloc((void **)&tl.d_etab, std::max<size_t>(etab_len, 4) * sizeof(double)));
   {
-    const size_t nthreads = (size_t)tt.size() * 3 * tl.P;
+    const size_t nthreads = (size_t)tt.size() * tl.P;
     etab_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, s>>>(tl.d_ttasks, d_tasks, (int)tt.size(), tl.P,
                                                                   h[0], h[1], h[2], tl.d_etab);
   }
@@ -469,7 +473,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   const size_t npairs = start[nbuckets];
   B200_ASSERT(npairs < ((size_t)1 << 31), "too many (task, block) pairs on one level");
   tl.npairs = (long long)npairs;
-  B200_CHECK(cudaMalloc((void **)&tl.d_pairs, std::max<size_t>(npairs, 1) * sizeof(TPair)));
+  B200_CHECK(cudaMalloc((void **)&tl.d_pairs, (npairs + kPairPad) * sizeof(TPair)));
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
   unsigned long long *d_keys[2] = {nullptr, nullptr};
   TPair *d_pairs_alt = nullptr;
@@ -489,7 +493,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   // also makes the accumulation order (and so the results) reproducible.
   if (npairs > 1) {
     B200_CHECK(cudaMalloc((void **)&d_keys[1], npairs * sizeof(unsigned long long)));
-    B200_CHECK(cudaMalloc((void **)&d_pairs_alt, npairs * sizeof(TPair)));
+    B200_CHECK(cudaMalloc((void **)&d_pairs_alt, (npairs + kPairPad) * sizeof(TPair)));
     cub::DoubleBuffer<unsigned long long> kb(d_keys[0], d_keys[1]);
     cub::DoubleBuffer<uint4> vb((uint4 *)tl.d_pairs, (uint4 *)d_pairs_alt);
     void *d_sort_temp = nullptr;
@@ -505,6 +509,10 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
     cudaFree(d_sort_temp);
   }
   cudaFree(d_keys[0]), cudaFree(d_keys[1]), cudaFree(d_pairs_alt);
+  if (npairs > 0)
+    for (int i = 0; i < kPairPad; i++)
+      B200_CHECK(cudaMemcpyAsync(tl.d_pairs + npairs + i, tl.d_pairs + npairs - 1, sizeof(TPair),
+                                 cudaMemcpyDeviceToDevice, s));
 
   // work items per lp class: a block's pairs of that class (contiguous, ordered by lp) cut into chunks
   std::vector<TWork> work;
@@ -705,12 +713,12 @@ template <int LP> __device__ __forceinline__ void load_row(const double *__restr
   default: BODY(14) BODY(15)                                                   \
   }
 
-// Sign-extended byte at bit position `pos` of `v`.
-__device__ __forceinline__ int sext_byte(const unsigned v, const unsigned pos) {
-  int r;
-  asm("bfe.s32 %0, %1, %2, 8;" : "=r"(r) : "r"(v), "r"(pos));
-  return r;
-}
+// Sign-extended byte of `v` that a left shift by `sh` moves to the top.
+__device__ __forceinline__ int top_byte(const unsigned v, const unsigned sh) { return (int)(v << sh) >> 24; }
+
+// The kernels' dynamic shared memory, addressed through the symbol (an index, not a
+// generic pointer: the compiler then folds the window base into the LDS/STS).
+extern __shared__ double tiled_smem[];
 
 // Per-lane constants of the pair loops.
 struct LaneCtx {
@@ -718,12 +726,14 @@ struct LaneCtx {
   const double *__restrict__ etab;       // exp tables of the level
   const double *__restrict__ coef_lane;  // coef + coef_base + lane
   double *__restrict__ coef0;            // coef + coef_base
-  const unsigned char *__restrict__ ktab_lane;  // ktab + lj * kKPitch + li
-  const unsigned short *__restrict__ s_zm;      // shared copy of the plane-mask table (biased)
-  double *__restrict__ ws;               // this warp's scratch (two stages)
+  const unsigned char *__restrict__ ktab;
+  int zm_index;                          // plane-mask table (biased) in tiled_smem, in 16-bit units
+  int ws_index;                          // this warp's scratch (two stages) in tiled_smem, in doubles
   double my_h;
   int my_axis, my_t;
-  unsigned sel;                          // bit position of my axis' byte in opk
+  int emul, eadd;                        // my table entry: 4 * (epack >> 5) + nbq * emul + eadd - o
+  int klane;                             // lj * kKPitch + li
+  unsigned sel;                          // left shift that moves my axis' byte of opk to the top
   int tt_first, coef_stride;
   int lane, li, lj;
 };
@@ -751,30 +761,35 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
   int o_n;
 #define B200_FETCH(R)                                                          \
   {                                                                            \
-    o_n = sext_byte(R.z, c.sel);                                               \
-    const int nbq_ = (int)(R.w & 31u), pq_ = 2 * nbq_ + 5;                     \
-    const int ge_ = min(max(c.my_t + nbq_ + 1 - o_n, 0), pq_ - 2);             \
-    const double *row_ = c.etab + 2 * (size_t)(R.w >> 5) + c.my_axis * pq_;    \
-    roff_n = __ldg(row_);                                                      \
-    e_n = __ldg(row_ + 1 + ge_);                                               \
+    o_n = top_byte(R.z, c.sel);                                                \
+    const unsigned base_ = (R.w >> 3) & ~3u;                                   \
+    const int ge_ = (int)(R.w & 31u) * c.emul + c.eadd - o_n;                  \
+    roff_n = __ldg(c.etab + (base_ + (unsigned)c.my_axis));                    \
+    e_n = __ldg(c.etab + (base_ + (unsigned)ge_));                             \
     if (COLLOCATE) {                                                           \
       const double *c_ = c.coef_lane + ((int)R.x - c.tt_first) * c.coef_stride; \
       _Pragma("unroll") for (int k = 0; k < NCL; k++)                          \
         c_n[k] = (lane + 32 * k < NC) ? c_[32 * k] : 0.0;                      \
     }                                                                          \
   }
+  const uint4 *pp = c.pairs + first;
+  const uint4 *const pend = c.pairs + last;
   {
-    const uint4 Rf = c.pairs[first];
+    const uint4 Rf = pp[0];
     B200_FETCH(Rf)
   }
 
-  for (int ip = first; ip < last; ip++) {
-    const uint4 R0 = c.pairs[ip];                        // L1 hit (read as Rn one iteration ago)
-    const uint4 Rn = c.pairs[min(ip + 1, last - 1)];     // same line 7 times out of 8
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(c.pairs + min(ip + 8, last - 1)));
+  // The pair array is padded with kPairPad copies of its last record: the loop reads one
+  // record ahead and prefetches eight ahead without clamping.
+  int stage = 0;
+  for (; pp < pend; pp++) {
+    const uint4 R0 = pp[0];                              // L1 hit (read as Rn one iteration ago)
+    const uint4 Rn = pp[1];                              // same line 7 times out of 8
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + 8));
 
     // scratch: my table entry times the powers of (x - xp); the coefficients
-    double *ws = c.ws + (ip & 1) * STAGE;
+    double *ws = tiled_smem + c.ws_index + stage;
+    stage = STAGE - stage;
     {
       const double x = (double)(c.my_t - o_n) * c.my_h - roff_n;
       double *row = ws + lane * PITCH;
@@ -798,16 +813,18 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
             ws[32 * PITCH + lane + 32 * k] = c_n[k];
       }
     }
-    // (the tail re-fetches the last pair: harmless, and the loop stays branch-free)
+    // (the tail fetches for the record after the run -- the next run's first pair or
+    // the padding: harmless, and the loop stays branch-free)
     B200_FETCH(Rn)
 
     // sphere masks of my two columns: K+1 from the sphere table, then the plane mask
-    const unsigned char *kp = c.ktab_lane + R0.y;
+    const unsigned char *kp = c.ktab + (R0.y + (unsigned)c.klane);
     const unsigned k0 = __ldg(kp), k1 = __ldg(kp + 4 * kKPitch);
-    const int ozb = sext_byte(R0.z, 16u);  // oz; the table pointer is biased
-    const unsigned mask0 = c.s_zm[(int)(k0 * kZmPitch) + ozb];
-    const unsigned mask1 = c.s_zm[(int)(k1 * kZmPitch) + ozb];
-    const int wlo = (int)((R0.z >> 24) & 15u), whi = (int)(R0.z >> 28);
+    const int ozb = (int)R0.z >> 24;  // oz; the table index is biased
+    const unsigned short *s_zm = reinterpret_cast<const unsigned short *>(tiled_smem) + c.zm_index;
+    const unsigned mask0 = s_zm[(int)(k0 * kZmPitch) + ozb];
+    const unsigned mask1 = s_zm[(int)(k1 * kZmPitch) + ozb];
+    const int wlo = (int)((R0.z >> 16) & 15u), whi = (int)((R0.z >> 20) & 15u);
     __syncwarp();
 
     const double *tZ = ws + 16 * PITCH;
@@ -888,7 +905,7 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
 
 template <bool COLLOCATE, int LPLO, int LPHI>
 __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kernel(const TiledArgs A) {
-  extern __shared__ double smem[];
+  double *const smem = tiled_smem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int STAGE = stage_doubles(LPHI);
   unsigned short *s_zm = (unsigned short *)(smem + (size_t)kTiledWarps * 2 * STAGE);
@@ -902,16 +919,22 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kern
   const int my_axis = (lane < 8) ? 0 : ((lane < 16) ? 1 : 2);
   c.my_t = (lane < 8) ? lane : ((lane < 16) ? lane - 8 : lane - 16);
   c.my_h = (my_axis == 0) ? A.hx : ((my_axis == 1) ? A.hy : A.hz);
-  c.sel = 8u * my_axis;
+  c.sel = (my_axis == 0) ? 24u : ((my_axis == 1) ? 16u : 0u);
   c.my_axis = my_axis;
   c.etab = A.etab;
+  c.emul = 2 * my_axis + 1;                                  // axis * (2 nbq + 16) + nbq
+  c.eadd = 16 * my_axis + 4 + ((my_axis == 2) ? 15 : 7) + c.my_t;
   c.coef0 = A.coef + A.coef_base;
   c.coef_lane = c.coef0 + lane;
   c.tt_first = A.tt_first, c.coef_stride = A.coef_stride;
   c.pairs = (const uint4 *)A.pairs;
-  c.ktab_lane = A.ktab + c.lj * kKPitch + c.li;
-  c.s_zm = s_zm + kZmBias;
-  c.ws = smem + (size_t)warp * 2 * STAGE;
+  c.ktab = A.ktab;
+  c.klane = c.lj * kKPitch + c.li;
+  // Opaque to the compiler from here on: it would otherwise re-derive these per-lane
+  // constants from the thread index inside the pair loops (9 instructions for eadd alone).
+  asm volatile("" : "+r"(c.eadd), "+r"(c.klane), "+r"(c.sel));
+  c.zm_index = kTiledWarps * 2 * STAGE * 4 + kZmBias;
+  c.ws_index = warp * 2 * STAGE;
 
   // persistent warps: work items are handed out in spatial order
   for (;;) {

@@ -11,10 +11,12 @@ python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_$TAG.log 2>&1
-ncu --set full --clock-control none -k regex:"tiled_kernel" -s 16 -c 16 -o /tmp/prof_$TAG -f \
+# 14 tiled launches per step (7 collocate + 7 integrate): skip the warm-up step, capture the next
+ncu --set full --clock-control none -k regex:"tiled_kernel" -s 14 -c 14 -o /tmp/prof_$TAG -f \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/prof_$TAG.log 2>&1
 python tools/ncu_summary.py /tmp/prof_$TAG.ncu-rep > gpurun_out/ncu_tiled_$TAG.txt 2>&1
 ncu -i /tmp/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_tiled_${TAG}_raw.csv 2>/dev/null
+python tools/traffic_from_ncu.py gpurun_out/ncu_tiled_${TAG}_raw.csv H2O-256 > gpurun_out/traffic_$TAG.json
 ncu --set full --clock-control none -k regex:"pab_to_coef|coef_to_hab" -s 2 -c 2 -o /tmp/prof_coef_$TAG -f \
   python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/prof_coef_$TAG.log 2>&1
 python tools/ncu_summary.py /tmp/prof_coef_$TAG.ncu-rep > gpurun_out/ncu_coef_$TAG.txt 2>&1
