@@ -774,8 +774,11 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
   }
   const uint4 *pp = c.pairs + first;
   const uint4 *const pend = c.pairs + last;
+  // (opaque: kept in a vector register pair; as a uniform register ptxas copies it
+  // into fresh vector registers for every one of the loop's loads)
+  asm volatile("" : "+l"(pp));
   {
-    const uint4 Rf = pp[0];
+    const uint4 Rf = __ldg(pp);
     B200_FETCH(Rf)
   }
 
@@ -783,8 +786,8 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
   // record ahead and prefetches eight ahead without clamping.
   int stage = 0;
   for (; pp < pend; pp++) {
-    const uint4 R0 = pp[0];                              // L1 hit (read as Rn one iteration ago)
-    const uint4 Rn = pp[1];                              // same line 7 times out of 8
+    const uint4 R0 = __ldg(pp);                          // L1 hit (read as Rn one iteration ago)
+    const uint4 Rn = __ldg(pp + 1);                      // same line 7 times out of 8
     asm volatile("prefetch.global.L1 [%0];" ::"l"(pp + 8));
 
     // scratch: my table entry times the powers of (x - xp); the coefficients
