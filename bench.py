@@ -64,6 +64,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.recording = False  # the thread is started early (NVML init); samples count once armed
 
     def _nvml_loop(self):
         """NVML polled every 10 ms (an nvidia-smi process per sample takes longer than
@@ -77,9 +78,10 @@ class ClockSampler(threading.Thread):
             nv.nvmlDeviceGetCurrentClocksThrottleReasons
         bits = [0x8, 0x40, 0x20, 0x4]  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
         while not self._stop_evt.is_set():
-            r = int(get_reasons(h))
-            self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(vmax)]
-                                + ["Active" if r & b else "Not Active" for b in bits])
+            if self.recording:
+                r = int(get_reasons(h))
+                self.samples.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(vmax)]
+                                    + ["Active" if r & b else "Not Active" for b in bits])
             self._stop_evt.wait(0.01)
 
     def run(self):
@@ -93,7 +95,7 @@ class ClockSampler(threading.Thread):
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 p = [x.strip() for x in out.strip().split(",")]
-                if len(p) >= 6:
+                if len(p) >= 6 and self.recording:
                     self.samples.append(p)
             except Exception:
                 pass
@@ -355,14 +357,15 @@ def main():
         torch.cuda.synchronize()
 
     lib.set_device_resident(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     launches0 = lib.launch_count()
     for _ in range(args.warmup):
         step_resident()
     barrier()
     launches_per_step = (lib.launch_count() - launches0) // max(args.warmup, 1) if args.warmup else None
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.recording = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.launch_count()
     e0.record()

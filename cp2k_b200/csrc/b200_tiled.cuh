@@ -724,7 +724,6 @@ extern __shared__ double tiled_smem[];
 struct LaneCtx {
   const uint4 *__restrict__ pairs;
   const double *__restrict__ etab;       // exp tables of the level
-  const double *__restrict__ coef_lane;  // coef + coef_base + lane
   double *__restrict__ coef0;            // coef + coef_base
   const unsigned char *__restrict__ ktab;
   int zm_index;                          // plane-mask table (biased) in tiled_smem, in 16-bit units
@@ -767,7 +766,7 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
     roff_n = __ldg(c.etab + (base_ + (unsigned)c.my_axis));                    \
     e_n = __ldg(c.etab + (base_ + (unsigned)ge_));                             \
     if (COLLOCATE) {                                                           \
-      const double *c_ = c.coef_lane + ((int)R.x - c.tt_first) * c.coef_stride; \
+      const double *c_ = c.coef0 + ((R.x - (unsigned)c.tt_first) * (unsigned)c.coef_stride + (unsigned)lane); \
       _Pragma("unroll") for (int k = 0; k < NCL; k++)                          \
         c_n[k] = (lane + 32 * k < NC) ? c_[32 * k] : 0.0;                      \
     }                                                                          \
@@ -881,7 +880,7 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
 #undef B200_BODY
       // table entries outside the cube are zero and inactive columns have S = 0:
       // nothing spurious enters the warp-wide sums
-      double *__restrict__ gcoef = c.coef0 + ((int)R0.x - c.tt_first) * c.coef_stride;
+      double *__restrict__ gcoef = c.coef0 + (R0.x - (unsigned)c.tt_first) * (unsigned)c.coef_stride;
       if constexpr (LP <= 3) {
         // few coefficients: one transposing reduction over all of them
         double part[NC];
@@ -928,7 +927,6 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kern
   c.emul = 2 * my_axis + 1;                                  // axis * (2 nbq + 16) + nbq
   c.eadd = 16 * my_axis + 4 + ((my_axis == 2) ? 15 : 7) + c.my_t;
   c.coef0 = A.coef + A.coef_base;
-  c.coef_lane = c.coef0 + lane;
   c.tt_first = A.tt_first, c.coef_stride = A.coef_stride;
   c.pairs = (const uint4 *)A.pairs;
   c.ktab = A.ktab;

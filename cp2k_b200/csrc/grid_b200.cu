@@ -926,7 +926,14 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
 
   ScopedTimer *tm_grid = new ScopedTimer(T_INTEGRATE, s);
   B200_CHECK(cudaEventRecord(tl.ev_fork, s));
-  for (int l = 0; l < nlevels; l++) {
+  // Host-authoritative grids are uploaded coarsest level first: its kernels start after a
+  // few microseconds of copy and the big uploads overlap with compute.  (Resident grids:
+  // finest level first, so that the short kernels fill the tail.)
+  bool any_upload = false;
+  for (int l = 0; l < nlevels; l++)
+    any_upload = any_upload || !(g_device_resident && use_caller_device(grids[l]));
+  for (int k = 0; k < nlevels; k++) {
+    const int l = any_upload ? nlevels - 1 - k : k;
     const LevelDev &L = tl.levels[l];
     LevelInfo &li = tl.linfo[l];
     const size_t npts = (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2];
