@@ -46,7 +46,16 @@
 
 namespace b200 {
 
-constexpr int kBX = 8, kBY = 8, kBZ = 16;     // block (warp footprint)
+#ifndef B200_KBZ
+#define B200_KBZ 16
+#endif
+#ifndef B200_CTAS_LO
+#define B200_CTAS_LO 4
+#endif
+#ifndef B200_CTAS_HI
+#define B200_CTAS_HI 3
+#endif
+constexpr int kBX = 8, kBY = 8, kBZ = B200_KBZ;  // block (warp footprint)
 constexpr int kTiledThreads = 128;            // 4 autonomous warps
 constexpr int kTiledWarps = kTiledThreads / 32;
 constexpr int kTiledMaxLp = 6;                // max la_max + lb_max of a tiled task; beyond: generic kernels
@@ -701,6 +710,7 @@ template <int LP> __device__ __forceinline__ void load_row(const double *__restr
 
 // The 16 planes of a block in pairs, entered at the first pair any lane needs
 // and left after the last one (both warp-uniform, precomputed per pair).
+#if B200_KBZ == 16
 #define B200_PLANES(BODY)                                                      \
   switch (wlo >> 1) {                                                          \
   case 0: BODY(0) BODY(1) if (whi <= 1) break;                                 \
@@ -712,6 +722,15 @@ template <int LP> __device__ __forceinline__ void load_row(const double *__restr
   case 6: BODY(12) BODY(13) if (whi <= 13) break;                              \
   default: BODY(14) BODY(15)                                                   \
   }
+#else
+#define B200_PLANES(BODY)                                                      \
+  switch (wlo >> 1) {                                                          \
+  case 0: BODY(0) BODY(1) if (whi <= 1) break;                                 \
+  case 1: BODY(2) BODY(3) if (whi <= 3) break;                                 \
+  case 2: BODY(4) BODY(5) if (whi <= 5) break;                                 \
+  default: BODY(6) BODY(7)                                                     \
+  }
+#endif
 
 // Sign-extended byte of `v` that a left shift by `sh` moves to the top.
 __device__ __forceinline__ int top_byte(const unsigned v, const unsigned sh) { return (int)(v << sh) >> 24; }
@@ -906,7 +925,7 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
 }
 
 template <bool COLLOCATE, int LPLO, int LPHI>
-__global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? 4 : 3) tiled_kernel(const TiledArgs A) {
+__global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B200_CTAS_HI) tiled_kernel(const TiledArgs A) {
   double *const smem = tiled_smem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int STAGE = stage_doubles(LPHI);

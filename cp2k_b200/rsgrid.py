@@ -166,6 +166,40 @@ def _p2p(ops, dist):
             req.wait()
 
 
+def _runs(idx: np.ndarray) -> List[Tuple[int, int, int]]:
+    """Split an index array into maximal runs of consecutive values:
+    (position in idx, first value, length)."""
+    if idx.size == 0:
+        return []
+    cuts = np.concatenate([[0], np.nonzero(np.diff(idx) != 1)[0] + 1, [idx.size]])
+    return [(int(a), int(idx[a]), int(b - a)) for a, b in zip(cuts[:-1], cuts[1:])]
+
+
+def _rank_plan(sl: SlabLevel, rank: int, world: int):
+    """This rank's part of the exchange plan, as contiguous plane ranges, computed once
+    per (level, rank, world) and cached on the level: the halo exchange runs every SCF
+    step and must not redo index arithmetic on the host.
+
+    sends: [(peer, a, b)]            local HALO planes [a, b) that `peer` owns
+    recvs: [(peer, n, [(k, d, m)])]  a message of n planes from `peer`; its planes
+                                     [k, k+m) belong to my OWNED local planes [d, d+m)
+    Messages between a pair of ranks are posted in the same order on both sides."""
+    cache = sl.__dict__.setdefault("_plans", {})
+    key = (rank, world)
+    if key not in cache:
+        plan = _exchange_plan(sl, world)
+        sends, recvs = [], []
+        for (src, dst), (src_idx, dst_idx) in sorted(plan.items()):
+            for a, b in _segments(src_idx):
+                i0 = int(np.searchsorted(src_idx, a))
+                if src == rank:
+                    sends.append((dst, a, b))
+                if dst == rank:
+                    recvs.append((src, b - a, _runs(dst_idx[i0: i0 + (b - a)])))
+        cache[key] = (sends, recvs)
+    return cache[key]
+
+
 def halo_sum(grid, sl: SlabLevel, rank: int, world: int, dist) -> None:
     """After collocate: add every rank's halo planes into their owners
     (realspace_grid_types.F:988-1204).  `grid` is the rank's local grid as a torch
@@ -177,24 +211,18 @@ def halo_sum(grid, sl: SlabLevel, rank: int, world: int, dist) -> None:
         if world > 1:
             dist.all_reduce(grid)
         return
-    plan = _exchange_plan(sl, world)
-    ops, recvs = [], []
-    for (src, dst), (src_idx, dst_idx) in sorted(plan.items()):
-        if src == rank:
-            for a, b in _segments(src_idx):
-                ops.append(dist.P2POp(dist.isend, grid[a:b].contiguous(), dst))
-        if dst == rank:
-            for (a, b) in _segments(src_idx):  # same segmentation as the sender
-                n = b - a
-                buf = torch.empty((n,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
-                first = int(dst_idx[np.searchsorted(src_idx, a)])
-                ops.append(dist.P2POp(dist.irecv, buf, src))
-                recvs.append((first, n, buf, dst_idx[np.searchsorted(src_idx, a): np.searchsorted(src_idx, a) + n]))
+    sends, recvs = _rank_plan(sl, rank, world)
+    ops, bufs = [], []
+    for peer, a, b in sends:
+        ops.append(dist.P2POp(dist.isend, grid[a:b], peer))  # z-plane ranges are contiguous
+    for peer, n, runs in recvs:
+        buf = torch.empty((n,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
+        ops.append(dist.P2POp(dist.irecv, buf, peer))
+        bufs.append((buf, runs))
     _p2p(ops, dist)
-    for first, n, buf, didx in recvs:
-        # destination planes of one sender segment are contiguous unless they wrap
-        for k, d in enumerate(didx):
-            grid[int(d)] += buf[k]
+    for buf, runs in bufs:
+        for k, d, m in runs:
+            grid[d: d + m] += buf[k: k + m]
     # the halo has been handed over: zero it so that a later sum is idempotent
     lo, hi = sl.owned[rank]
     grid[: sl.border] = 0
@@ -203,27 +231,25 @@ def halo_sum(grid, sl: SlabLevel, rank: int, world: int, dist) -> None:
 
 def halo_fill(grid, sl: SlabLevel, rank: int, world: int, dist) -> None:
     """Before integrate: copy the owners' planes into every rank's halo
-    (realspace_grid_types.F:1677-1893)."""
+    (realspace_grid_types.F:1677-1893): the halo sum's plan run backwards."""
     import torch
 
     if not sl.distributed:
         return
-    plan = _exchange_plan(sl, world)  # (halo holder, owner)
-    ops, recvs = [], []
-    for (holder, owner), (halo_idx, own_idx) in sorted(plan.items()):
-        if owner == rank:
-            for a, b in _segments(halo_idx):
-                i0 = np.searchsorted(halo_idx, a)
-                rows = own_idx[i0: i0 + (b - a)]
-                ops.append(dist.P2POp(dist.isend, grid[torch.as_tensor(rows, device=grid.device)].contiguous(),
-                                      holder))
-        if holder == rank:
-            for a, b in _segments(halo_idx):
-                buf = torch.empty((b - a,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
-                ops.append(dist.P2POp(dist.irecv, buf, owner))
-                recvs.append((a, b, buf))
+    sends, recvs = _rank_plan(sl, rank, world)  # roles swap: owners send, halo holders receive
+    ops, bufs = [], []
+    for peer, n, runs in recvs:
+        if len(runs) == 1:
+            _, d, m = runs[0]
+            ops.append(dist.P2POp(dist.isend, grid[d: d + m], peer))
+        else:  # the owned range wraps around the periodic boundary
+            ops.append(dist.P2POp(dist.isend, torch.cat([grid[d: d + m] for _, d, m in runs]), peer))
+    for peer, a, b in sends:
+        buf = torch.empty((b - a,) + tuple(grid.shape[1:]), dtype=grid.dtype, device=grid.device)
+        ops.append(dist.P2POp(dist.irecv, buf, peer))
+        bufs.append((a, b, buf))
     _p2p(ops, dist)
-    for a, b, buf in recvs:
+    for a, b, buf in bufs:
         grid[a:b] = buf
 
 
