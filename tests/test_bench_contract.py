@@ -1,0 +1,41 @@
+"""CPU-side checks of bench.py's contract: the reference arm (the unmodified
+reference CPU backend from oracle/_ref) prints one JSON line with the keys the
+driver reads, and the product arm refuses to run without a CUDA device (there is
+no CPU fallback to fall into)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_line(reference):
+    out = _run("--impl", "reference", "--workload", "H2O-64", "--steps", "1", "--warmup", "1", "--cpu-budget", "2")
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "GFLOP/s" and d["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["dtype"] == "f64" and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box WITHOUT a GPU")
+def test_product_arm_fails_loudly_without_gpu():
+    out = _run("--workload", "H2O-64", "--steps", "1", "--warmup", "1", "--no-cpu-baseline")
+    assert out.returncode != 0
+    assert not any(l.startswith("{") for l in out.stdout.splitlines())  # no number without the device
