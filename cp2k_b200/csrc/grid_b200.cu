@@ -137,6 +137,12 @@ struct LevelInfo {
   TiledLevel tiled;                  // tiled-path data (b200_tiled.cuh)
 };
 
+constexpr int kNumSizeClasses = 3;
+inline int size_class(const TaskDev &T) {
+  const int lp0 = T.la_max + T.lb_max;
+  return lp0 <= 1 ? 0 : (lp0 == 2 ? 1 : 2);
+}
+
 struct TaskList {
   bool empty = true;
   bool ortho = false;
@@ -174,7 +180,18 @@ struct TaskList {
   struct Chunk {
     int t0, t1;        // range in the by-block task order
     size_t off0;       // first double of the chunk in the block buffers
+    int c0[kNumSizeClasses + 1];  // the chunk's tasks per size class: ranges in d_class_ids_chunked
   };
+  // The coefficient kernels size their per-task scratch in shared memory for the largest
+  // task of a launch; tasks are therefore launched per SIZE CLASS (by la_max + lb_max), so
+  // that the many small products are not throttled to the occupancy of the few large ones.
+  struct SizeClass {
+    int max_nsgf_set = 1, max_ncoset_raw = 1, max_la = 0, max_lb = 0;
+  };
+  SizeClass sclass[kNumSizeClasses];
+  DevBuf<int> d_class_ids_chunked;  // per chunk: class 0 | class 1 | class 2, block order inside
+  DevBuf<int> d_class_ids_global;   // whole list: class 0 | class 1 | class 2, block order inside
+  int g0[kNumSizeClasses + 1] = {0};
   std::vector<Chunk> chunks;
   cudaStream_t copy_stream = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
@@ -207,6 +224,9 @@ struct TaskList {
     chunks.clear();
     d_tasks.release(), d_sphi.release(), d_iota.release(), d_generic_ids.release();
     d_block_task_ids.release(), d_block_first.release();
+    d_class_ids_chunked.release(), d_class_ids_global.release();
+    for (auto &c : sclass)
+      c = SizeClass();
     for (auto &b : d_coef_off)
       b.release();
     d_coef.release(), d_pab.release(), d_hab.release(), d_fv.release();
@@ -583,6 +603,12 @@ static void build_task_list(
       li.max_lp0_general = std::max(li.max_lp0_general, lp0);
     tl.max_nsgf_set = std::max({tl.max_nsgf_set, T.nsgf_seta, T.nsgf_setb});
     tl.max_ncoset_raw = std::max({tl.max_ncoset_raw, T.ncoseta, T.ncosetb});
+    {
+      TaskList::SizeClass &C = tl.sclass[size_class(T)];
+      C.max_nsgf_set = std::max({C.max_nsgf_set, T.nsgf_seta, T.nsgf_setb});
+      C.max_ncoset_raw = std::max({C.max_ncoset_raw, T.ncoseta, T.ncosetb});
+      C.max_la = std::max(C.max_la, T.la_max), C.max_lb = std::max(C.max_lb, T.lb_max);
+    }
     tl.max_la = std::max(tl.max_la, T.la_max);
     if (std::find(tl.l_combos.begin(), tl.l_combos.end(), std::make_pair(T.la_max, T.lb_max)) ==
         tl.l_combos.end())
@@ -630,8 +656,29 @@ static void build_task_list(
       const int b1 = (int)((long long)nblocks * (c + 1) / nchunks);
       if (b1 > b0)
         tl.chunks.push_back(TaskList::Chunk{block_first[b0], block_first[b1],
-                                            (c == 0) ? (size_t)0 : (size_t)block_offsets[b0]});
+                                            (c == 0) ? (size_t)0 : (size_t)block_offsets[b0], {0, 0, 0, 0}});
     }
+    // size-class lists (block order inside a class)
+    std::vector<int> chunked, global;
+    chunked.reserve(ntasks), global.reserve(ntasks);
+    for (auto &ch : tl.chunks)
+      for (int k = 0; k < kNumSizeClasses; k++) {
+        ch.c0[k] = (int)chunked.size();
+        for (int it = ch.t0; it < ch.t1; it++)
+          if (size_class(tl.h_tasks[by_block[it]]) == k)
+            chunked.push_back(by_block[it]);
+        ch.c0[k + 1] = (int)chunked.size();
+      }
+    for (int k = 0; k < kNumSizeClasses; k++) {
+      tl.g0[k] = (int)global.size();
+      for (int it = 0; it < ntasks; it++)
+        if (size_class(tl.h_tasks[by_block[it]]) == k)
+          global.push_back(by_block[it]);
+      tl.g0[k + 1] = (int)global.size();
+    }
+    B200_ASSERT((int)chunked.size() == ntasks && (int)global.size() == ntasks, "size-class lists incomplete");
+    tl.d_class_ids_chunked.upload(chunked, s);
+    tl.d_class_ids_global.upload(global, s);
     B200_CHECK(cudaStreamCreateWithFlags(&tl.copy_stream, cudaStreamNonBlocking));
     B200_CHECK(cudaEventCreateWithFlags(&tl.ev_copy_done, cudaEventDisableTiming));
     tl.ev_chunk.resize(tl.chunks.size());
@@ -800,8 +847,13 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   if (g_device_resident && use_caller_device(pab_blocks)) {
     d_pab = pab_blocks->device_buffer;
     ScopedTimer tm(T_PAB2COEF, s);
-    launch_pab_to_coef(CL, func, d_pab, tl.max_nsgf_set, tl.max_ncoset_raw,
-                       tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
+    for (int k = 0; k < kNumSizeClasses; k++) {
+      const TaskList::SizeClass &C = tl.sclass[k];
+      CL.task_ids = tl.d_class_ids_global.p + tl.g0[k];
+      CL.ntasks = tl.g0[k + 1] - tl.g0[k];
+      launch_pab_to_coef(CL, func, d_pab, C.max_nsgf_set, C.max_ncoset_raw, C.max_la + F.dla_max,
+                         C.max_lb + F.dlb_max);
+    }
   } else {
     double *dst = use_caller_device(pab_blocks) ? pab_blocks->device_buffer : nullptr;
     if (dst == nullptr) {
@@ -821,10 +873,13 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
                                    cudaMemcpyHostToDevice, tl.copy_stream));
       B200_CHECK(cudaEventRecord(tl.ev_chunk[c], tl.copy_stream));
       B200_CHECK(cudaStreamWaitEvent(s, tl.ev_chunk[c], 0));
-      CL.task_ids = tl.d_block_task_ids.p + tl.chunks[c].t0;
-      CL.ntasks = tl.chunks[c].t1 - tl.chunks[c].t0;
-      launch_pab_to_coef(CL, func, d_pab, tl.max_nsgf_set, tl.max_ncoset_raw,
-                         tl.max_la + F.dla_max, tl.max_lb + F.dlb_max);
+      for (int k = 0; k < kNumSizeClasses; k++) {
+        const TaskList::SizeClass &C = tl.sclass[k];
+        CL.task_ids = tl.d_class_ids_chunked.p + tl.chunks[c].c0[k];
+        CL.ntasks = tl.chunks[c].c0[k + 1] - tl.chunks[c].c0[k];
+        launch_pab_to_coef(CL, func, d_pab, C.max_nsgf_set, C.max_ncoset_raw, C.max_la + F.dla_max,
+                           C.max_lb + F.dlb_max);
+      }
     }
   }
 
@@ -1014,15 +1069,24 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   HL.max_la_l = tl.max_la + dla_max, HL.max_lb_l = tl.max_lb + dlb_max, HL.stream = s;
   if (hab_resident) {
     ScopedTimer tm(T_COEF2HAB, s);
-    launch_coef_to_hab(HL, tl.ntasks, tl.max_ncoset_raw, dla_max, dla_min, dlb_max, dlb_min);
+    for (int k = 0; k < kNumSizeClasses; k++) {
+      const TaskList::SizeClass &C = tl.sclass[k];
+      HL.block_task_ids = tl.d_class_ids_global.p + tl.g0[k];
+      HL.max_nsgf_set = C.max_nsgf_set, HL.max_la_l = C.max_la + dla_max, HL.max_lb_l = C.max_lb + dlb_max;
+      launch_coef_to_hab(HL, tl.g0[k + 1] - tl.g0[k], C.max_ncoset_raw, dla_max, dla_min, dlb_max, dlb_min);
+    }
   } else {
     // chunk-wise: the download of finished blocks overlaps the remaining kernels
     const size_t total = hab_blocks->size / sizeof(double);
     ScopedTimer tm(T_COEF2HAB, s);
     for (size_t c = 0; c < tl.chunks.size(); c++) {
-      HL.block_task_ids = tl.d_block_task_ids.p + tl.chunks[c].t0;
-      launch_coef_to_hab(HL, tl.chunks[c].t1 - tl.chunks[c].t0, tl.max_ncoset_raw, dla_max, dla_min,
-                         dlb_max, dlb_min);
+      for (int k = 0; k < kNumSizeClasses; k++) {
+        const TaskList::SizeClass &C = tl.sclass[k];
+        HL.block_task_ids = tl.d_class_ids_chunked.p + tl.chunks[c].c0[k];
+        HL.max_nsgf_set = C.max_nsgf_set, HL.max_la_l = C.max_la + dla_max, HL.max_lb_l = C.max_lb + dlb_max;
+        launch_coef_to_hab(HL, tl.chunks[c].c0[k + 1] - tl.chunks[c].c0[k], C.max_ncoset_raw, dla_max, dla_min,
+                           dlb_max, dlb_min);
+      }
       B200_CHECK(cudaEventRecord(tl.ev_chunk[c], s));
       B200_CHECK(cudaStreamWaitEvent(tl.copy_stream, tl.ev_chunk[c], 0));
       const size_t o0 = tl.chunks[c].off0;
