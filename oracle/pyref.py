@@ -23,6 +23,10 @@ from cp2k_b200.grid_api import (GRID_BACKEND_CPU, GRID_BACKEND_REF, GridLibrary,
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libgrid_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libgrid_ref.so")
+# the same reference library with INTEGRATION.md's dispatcher patch (oracle/patch_dispatcher.py):
+# its public API reaches the product library as GRID_BACKEND_B200
+REF_B200_SO = os.path.join(HERE, "_ref", "libgrid_ref_b200.so")
+GRID_BACKEND_B200 = 15
 
 
 def build(quiet: bool = True) -> None:
@@ -68,8 +72,9 @@ class ReferenceLibrary(GridLibrary):
     """The reference's public, dispatching ABI (src/grid/grid_task_list.h:59-126):
     same arguments as the per-backend one plus ``npts_local`` on every call."""
 
-    def __init__(self, backend: int = GRID_BACKEND_REF):
-        super().__init__(REF_SO, "grid")
+    def __init__(self, backend: int = GRID_BACKEND_REF, path: str = REF_SO):
+        super().__init__(path, "grid")
+        self.path = path
         L = self.lib
         L.grid_library_init.restype = None
         L.grid_library_set_config.restype = None
@@ -84,11 +89,15 @@ class ReferenceLibrary(GridLibrary):
         L.grid_replay.restype = C.c_bool
         L.grid_replay.argtypes = [C.c_char_p, C.c_int, C.c_bool, C.c_bool, C.c_int, C.c_double]
 
-    def set_backend(self, backend: int) -> None:
-        """Affects task lists created afterwards (src/grid/grid_task_list.c:50-59)."""
-        assert backend in (GRID_BACKEND_REF, GRID_BACKEND_CPU)
+    def set_backend(self, backend: int, validate: bool = False) -> None:
+        """Affects task lists created afterwards (src/grid/grid_task_list.c:50-59).
+        ``validate`` switches on the dispatcher's own shadow run of the REF backend
+        after every call (1e-12 on grids and hab, 1e-8 on forces/virial; it aborts on a
+        mismatch, src/grid/grid_task_list.c:225-260, 352-420)."""
+        assert backend in (GRID_BACKEND_REF, GRID_BACKEND_CPU) or \
+            (backend == GRID_BACKEND_B200 and self.path == REF_B200_SO)
         self.backend = backend
-        self.lib.grid_library_set_config(backend, False, False)
+        self.lib.grid_library_set_config(backend, bool(validate), False)
 
     def _call_collocate(self, tl, func, pab, grids_arr):
         npl = _i32([l.npts_local for l in tl.layouts]).reshape(-1)
@@ -115,6 +124,19 @@ def load_oracle() -> OracleLibrary:
 
 def have_reference() -> bool:
     return os.path.exists(REF_SO)
+
+
+def have_reference_b200() -> bool:
+    return os.path.exists(REF_B200_SO)
+
+
+def load_reference_b200(validate: bool = True) -> ReferenceLibrary:
+    """The patched-dispatcher build, with the B200 backend selected."""
+    if "b200" not in _REFS:
+        _REFS["b200"] = ReferenceLibrary(GRID_BACKEND_B200, REF_B200_SO)
+    lib = _REFS["b200"]
+    lib.set_backend(GRID_BACKEND_B200, validate)
+    return lib
 
 
 def load_reference(backend: int = GRID_BACKEND_REF) -> ReferenceLibrary:
