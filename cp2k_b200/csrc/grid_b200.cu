@@ -715,8 +715,20 @@ static void build_task_list(
 // ---------------------------------------------------------------------------
 // buffers at the call boundary
 // ---------------------------------------------------------------------------
+// A caller's device_buffer is used only if it really is device (or managed) memory: a
+// reference build without __OFFLOAD fills offload_buffer.device_buffer from its memory pool
+// with a plain host allocation (src/offload/offload_buffer.c:78-83 with
+// OFFLOAD_BUFFER_MEMPOOL, src/offload/offload_mempool.c:69-106) -- non-NULL, but not a device
+// pointer.  Found by running the reference's own replay harness against this backend.
 static inline bool use_caller_device(const grid_b200_buffer *b) {
-  return b != nullptr && b->device_buffer != nullptr;
+  if (b == nullptr || b->device_buffer == nullptr)
+    return false;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, b->device_buffer) != cudaSuccess) {
+    cudaGetLastError();  // clear the sticky-free error of an unknown pointer
+    return false;
+  }
+  return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
 }  // namespace b200

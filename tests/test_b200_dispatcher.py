@@ -106,3 +106,39 @@ def test_reference_validate_mode_accepts_the_backend(b200):
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "VALIDATE_OK 13" in out.stdout
     assert out.stdout.count("Validated grid collocate") >= 13 and "Validation failure" not in out.stderr
+
+
+_REPLAY_SCRIPT = """
+import glob, os, sys
+sys.path.insert(0, {root!r})
+from oracle import pyref
+lib = pyref.load_reference_b200(validate=False)
+files = sorted(glob.glob(os.path.join({root!r}, "oracle", "_ref", "sample_tasks", "*.task")))
+bad = []
+for f in files:
+    for collocate in (True, False):
+        # grid_unittest.c:51-57 -- one cycle, batched (the dispatcher path), tolerance 1e-12
+        if not lib.lib.grid_replay(f.encode(), 1, collocate, True, 1, 1e-12):
+            bad.append((os.path.basename(f), collocate))
+print("REPLAY_DONE", len(files), bad)
+"""
+
+
+@pytest.mark.gpu
+def test_reference_unit_test_harness_on_the_backend(b200):
+    """BASELINE config 1: the reference's OWN replay harness (src/grid/grid_replay.c, the
+    engine of grid_unittest.x / grid_miniapp.x) reads its own 13 sample .task files and
+    checks the batched legs of its unit test (src/grid/grid_unittest.c:51-57) against the
+    values stored in the files -- with this backend doing the work."""
+    import glob
+    import subprocess
+    import sys
+
+    _pyref()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not glob.glob(os.path.join(root, "oracle", "_ref", "sample_tasks", "*.task")):
+        pytest.skip("oracle/_ref/sample_tasks not present (made by `make -C oracle ref_b200`)")
+    out = subprocess.run([sys.executable, "-c", _REPLAY_SCRIPT.format(root=root)], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert "REPLAY_DONE 13 []" in out.stdout, out.stdout[-3000:]
