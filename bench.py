@@ -179,10 +179,18 @@ def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0, virial=False)
     from cp2k_b200.grid_api import GRID_BACKEND_CPU, OffloadBuffer
     from oracle import pyref
 
+    # All host cores this process may use, whatever OMP_NUM_THREADS says (torchrun exports
+    # OMP_NUM_THREADS=1 to its workers); `cores` is what the OpenMP runtime then reports.
+    # Set BEFORE the reference library initialises: grid_library_init sizes its per-thread
+    # state from omp_get_max_threads() (src/grid/common/grid_library.c:53-67).
+    import ctypes
+
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    gomp = ctypes.CDLL("libgomp.so.1")
+    gomp.omp_set_num_threads(int(avail))
+    cores = int(gomp.omp_get_max_threads())
     lib = pyref.load_reference(GRID_BACKEND_CPU)
     ora = pyref.load_oracle()
-    cores = os.cpu_count() or 1
-    rng = np.random.default_rng(7)
 
     def one(sample_wl, nsteps, nwarm):
         tl = sample_wl.create(lib)

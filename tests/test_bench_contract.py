@@ -13,9 +13,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(*args):
+def _run(*args, env=None):
     return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
-                          cwd=ROOT, timeout=600)
+                          cwd=ROOT, timeout=600, env=env)
 
 
 def test_reference_arm_line(reference):
@@ -32,6 +32,21 @@ def test_reference_arm_line(reference):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_arm_uses_all_host_cores_under_torchrun_env(reference):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm must still time
+    the CPU backend on every core it may use and report that count."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = _run("--impl", "reference", "--gpus", "2", "--workload", "H2O-64", "--steps", "1", "--warmup", "0",
+               "--cpu-budget", "1", env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["n_gpus"] == 2
+    # the other ranks print nothing and exit 0
+    env["RANK"] = "1"
+    out = _run("--impl", "reference", "--gpus", "2", "--workload", "H2O-64", env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="needs a box WITHOUT a GPU")
