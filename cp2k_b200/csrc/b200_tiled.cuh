@@ -36,6 +36,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -564,7 +565,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   }
   tl.nwork = (int)work.size();
   up(&tl.d_work, work);
-  B200_CHECK(cudaMalloc((void **)&tl.d_counters, 2 * kNumClasses * sizeof(int)));
+  B200_CHECK(cudaMalloc((void **)&tl.d_counters, 2 * kNumClasses * 4 * sizeof(int)));
   B200_CHECK(cudaStreamSynchronize(s));
   cudaFree(d_temp), cudaFree(d_count), cudaFree(d_start);
 }
@@ -924,7 +925,7 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
 #undef B200_FETCH
 }
 
-template <bool COLLOCATE, int LPLO, int LPHI>
+template <bool COLLOCATE, int LPLO, int LPHI, int SUB = 0>
 __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B200_CTAS_HI) tiled_kernel(const TiledArgs A) {
   double *const smem = tiled_smem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -965,6 +966,10 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B2
     if (iw >= A.nwork)
       break;
     const int4 W0 = ((const int4 *)A.work)[2 * iw], W1 = ((const int4 *)A.work)[2 * iw + 1];
+    if constexpr (LPLO == LPHI) {  // experimental per-lp launches: only this lp's pairs of the item
+      if (((SUB == 0) ? W0.w : ((SUB == 1) ? W1.x : W1.y)) >= ((SUB == 0) ? W1.x : ((SUB == 1) ? W1.y : W1.z)))
+        continue;
+    }
     const int x0 = W0.x, y0 = W0.y, z0 = W0.z;
     const int vx = min(kBX, A.nx - x0), vy = min(kBY, A.ny - y0), vz = min(kBZ, A.nz - z0);
     const size_t sy = A.nx, sz = (size_t)A.nx * A.ny;
@@ -986,7 +991,11 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B2
       }
     }
 
-    run_pairs<COLLOCATE, LPLO, STAGE>(c, W0.w, W1.x, acc0, acc1);
+    if constexpr (LPLO == LPHI)
+      run_pairs<COLLOCATE, LPLO, STAGE>(c, (SUB == 0) ? W0.w : ((SUB == 1) ? W1.x : W1.y),
+                                        (SUB == 0) ? W1.x : ((SUB == 1) ? W1.y : W1.z), acc0, acc1);
+    else
+      run_pairs<COLLOCATE, LPLO, STAGE>(c, W0.w, W1.x, acc0, acc1);
     if constexpr (LPLO + 1 <= LPHI)
       run_pairs<COLLOCATE, LPLO + 1, STAGE>(c, W1.x, W1.y, acc0, acc1);
     if constexpr (LPLO + 2 <= LPHI)
@@ -1011,18 +1020,18 @@ inline size_t tiled_smem_bytes(const int lphi) {
          (size_t)kZmRows * kZmPitch * sizeof(unsigned short);
 }
 
-template <bool COLLOCATE, int LPLO, int LPHI>
+template <bool COLLOCATE, int LPLO, int LPHI, int SUB = 0>
 inline void launch_tiled_class(const TiledArgs &A, const TiledLevel &tl, cudaStream_t s) {
   (void)tl;
   const size_t bytes = tiled_smem_bytes(LPHI);
   B200_ASSERT(bytes <= 200 * 1024, "tiled kernel: shared memory budget exceeded");
-  B200_CHECK(cudaFuncSetAttribute(tiled_kernel<COLLOCATE, LPLO, LPHI>,
+  B200_CHECK(cudaFuncSetAttribute(tiled_kernel<COLLOCATE, LPLO, LPHI, SUB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   int per_sm = 1;
-  B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiled_kernel<COLLOCATE, LPLO, LPHI>,
+  B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiled_kernel<COLLOCATE, LPLO, LPHI, SUB>,
                                                           kTiledThreads, bytes));
   const int grid = std::min((A.nwork + kTiledWarps - 1) / kTiledWarps, 148 * std::max(per_sm, 1));
-  tiled_kernel<COLLOCATE, LPLO, LPHI><<<grid, kTiledThreads, bytes, s>>>(A);
+  tiled_kernel<COLLOCATE, LPLO, LPHI, SUB><<<grid, kTiledThreads, bytes, s>>>(A);
   B200_CHECK(cudaGetLastError());
   count_launch();
 }
@@ -1042,10 +1051,14 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
   A.nx = L.level.npts_local[0], A.ny = L.level.npts_local[1], A.nz = L.level.npts_local[2];
   A.hx = L.level.dh[0], A.hy = L.level.dh[4], A.hz = L.level.dh[8];
   unsigned leftover = 0u;
-  B200_CHECK(cudaMemsetAsync(tl.d_counters + (COLLOCATE ? 0 : kNumClasses), 0, kNumClasses * sizeof(int),
+  // GRID_B200_PER_LP=1 (experimental, off by default): one kernel per lp instead of one per
+  // lp class -- each lp loop then gets its own register allocation and a smaller scratch, at
+  // the price of flushing / loading a block once per lp.
+  static const bool per_lp = (getenv("GRID_B200_PER_LP") != nullptr && atoi(getenv("GRID_B200_PER_LP")) != 0);
+  B200_CHECK(cudaMemsetAsync(tl.d_counters + (COLLOCATE ? 0 : kNumClasses * 4), 0, kNumClasses * 4 * sizeof(int),
                              L.stream));
   for (int cls = 0; cls < kNumClasses; cls++) {
-    A.counter = tl.d_counters + (COLLOCATE ? 0 : kNumClasses) + cls;
+    A.counter = tl.d_counters + (COLLOCATE ? 0 : kNumClasses * 4) + cls * 4;
     A.work = tl.d_work + tl.class_work_first[cls];
     A.nwork = tl.class_work_first[cls + 1] - tl.class_work_first[cls];
     if (A.nwork == 0)
@@ -1059,6 +1072,17 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
     A.coef_base = tl.coef_base[L.dl][cls];
     A.coef_stride = ncoset(hi);
     cudaStream_t s = L.stream;
+    if (per_lp && lo == 0) {  // the dominant class only (water: lp 0..2)
+      int *const counter0 = A.counter;
+      A.counter = counter0 + 0;
+      launch_tiled_class<COLLOCATE, 0, 0, 0>(A, tl, s);
+      A.counter = counter0 + 1;
+      launch_tiled_class<COLLOCATE, 1, 1, 1>(A, tl, s);
+      A.counter = counter0 + 2;
+      launch_tiled_class<COLLOCATE, 2, 2, 2>(A, tl, s);
+      A.counter = counter0;
+      continue;
+    }
     if (lo == 0) launch_tiled_class<COLLOCATE, 0, 2>(A, tl, s);
     else if (lo == 1) launch_tiled_class<COLLOCATE, 1, 3>(A, tl, s);
     else if (lo == 2) launch_tiled_class<COLLOCATE, 2, 4>(A, tl, s);
