@@ -19,7 +19,9 @@
 //   * the separable Gaussian factors exp(-zetp (x-xp)^2) of every task are
 //     tabulated once per task list (they depend on geometry only) -- there is
 //     no exp() in the hot loop; a (pair, warp) step loads exactly one table
-//     entry per lane (8 x-, 8 y-, 16 z-entries);
+//     entry per lane (8 x-, 8 y-, 16 z-entries).  The rows are sized per task and
+//     zero-padded by the block extent, the pair array is padded with copies of its
+//     last record: the look-ahead loads and the table index need no clamping;
 //   * which points of a cube are inside the (discretised-radius) sphere is two
 //     table lookups per column: because the reference discretises the radius to
 //     n*drmin (ref/grid_ref_collint.h:237-239) the admissible z-extent K of a
