@@ -5,8 +5,8 @@ GRID_BACKEND_B200 = 15 (oracle/Makefile, target `ref_b200`).
 
 Nothing of the reference is stored in this repository: the script reads
 src/grid/grid_task_list.c and src/grid/grid_task_list_internal.h where they lie,
-inserts OUR lines at anchored positions and writes the result to the
-(git-ignored) build directory.  It fails loudly if an anchor is missing, i.e. if
+inserts OUR lines at anchored positions and writes the result to a temporary
+build directory that the Makefile removes after the compile.  It fails loudly if an anchor is missing, i.e. if
 the reference's dispatcher changed shape.
 
 Usage: python patch_dispatcher.py <reference>/src/grid <build dir>

@@ -38,6 +38,50 @@ def load_task(name: str) -> dict:
     return t
 
 
+def write_task_file(t: dict, path: str) -> None:
+    """Writes a golden fixture back in the reference's "#Grid task v10" text format
+    (written by src/grid/cpu/grid_cpu_collocate.c:47-139, read by
+    src/grid/grid_replay.c:242-349) so that the reference's own replay harness can
+    read it: the inverse of tests/golden/make_golden.py::parse."""
+    e = lambda x: "%.21e" % float(x)  # noqa: E731  (doubles round-trip exactly)
+    out = ["#Grid task v10"]
+    for k in ("orthorhombic", "border_mask", "func", "la_max", "la_min", "lb_max", "lb_min"):
+        out.append(f"{k} {int(t[k])}")
+    for k in ("zeta", "zetb", "rscale"):
+        out.append(f"{k} {e(t[k])}")
+    for k in ("dh", "dh_inv"):
+        for i in range(3):
+            out.append(f"{k} {i} " + " ".join(e(x) for x in t[k][i]))
+    for k in ("ra", "rab"):
+        out.append(f"{k} " + " ".join(e(x) for x in t[k]))
+    for k in ("npts_global", "npts_local", "shift_local", "border_width"):
+        out.append(f"{k} " + " ".join(str(int(x)) for x in t[k]))
+    out.append(f"radius {e(t['radius'])}")
+    for k in ("o1", "o2", "n1", "n2"):
+        out.append(f"{k} {int(t[k])}")
+    n1, n2 = int(t["n1"]), int(t["n2"])
+    for i in range(n2):
+        for j in range(n1):
+            out.append(f"pab {i} {j} {e(t['pab'][i, j])}")
+    nl = [int(x) for x in t["npts_local"]]
+    out.append(f"ngrid_nonzero {int(t['grid_idx'].size)}")
+    for idx, val in zip(t["grid_idx"], t["grid_val"]):
+        idx = int(idx)
+        i, j, k = idx % nl[0], (idx // nl[0]) % nl[1], idx // (nl[0] * nl[1])
+        out.append(f"grid {i} {j} {k} {e(val)}")
+    na, nb = ncoset(int(t["la_max"])), ncoset(int(t["lb_max"]))
+    for i in range(nb):
+        for j in range(na):
+            out.append(f"hab {int(t['o2']) + i} {int(t['o1']) + j} {e(t['hab'][i, j])}")
+    out.append("force_a " + " ".join(e(x) for x in t["force_a"]))
+    out.append("force_b " + " ".join(e(x) for x in t["force_b"]))
+    for i in range(3):
+        out.append(f"virial {i} " + " ".join(e(x) for x in t["virial"][i]))
+    out.append("#THE_END")
+    with open(path, "w") as fh:
+        fh.write("\n".join(out) + "\n")
+
+
 def golden_grid(t: dict) -> np.ndarray:
     g = np.zeros(int(np.prod(t["npts_local"])))
     g[t["grid_idx"]] = t["grid_val"]

@@ -113,7 +113,7 @@ import glob, os, sys
 sys.path.insert(0, {root!r})
 from oracle import pyref
 lib = pyref.load_reference_b200(validate=False)
-files = sorted(glob.glob(os.path.join({root!r}, "oracle", "_ref", "sample_tasks", "*.task")))
+files = sorted(glob.glob(os.path.join({tasks!r}, "*.task")))
 bad = []
 for f in files:
     for collocate in (True, False):
@@ -124,21 +124,41 @@ print("REPLAY_DONE", len(files), bad)
 """
 
 
+def _write_sample_tasks(directory):
+    """The 13 golden vectors back in the reference's `.task` text format (replay.write_task_file)."""
+    from replay import write_task_file
+
+    for name in TASK_NAMES:
+        write_task_file(load_task(name), os.path.join(str(directory), name + ".task"))
+
+
+def test_task_file_writer_feeds_the_reference_harness(reference, tmp_path):
+    """CPU check of the fixture writer: the unmodified reference's replay harness parses the
+    regenerated files and passes all four legs of its unit test (grid_unittest.c:51-57) with
+    its own backends."""
+    _write_sample_tasks(tmp_path)
+    lib = reference.load_reference()
+    for name in TASK_NAMES:
+        f = os.path.join(str(tmp_path), name + ".task").encode()
+        for collocate in (True, False):
+            for batch in (True, False):
+                assert lib.lib.grid_replay(f, 1, collocate, batch, 1, 1e-12), (name, collocate, batch)
+
+
 @pytest.mark.gpu
-def test_reference_unit_test_harness_on_the_backend(b200):
+def test_reference_unit_test_harness_on_the_backend(b200, tmp_path):
     """BASELINE config 1: the reference's OWN replay harness (src/grid/grid_replay.c, the
-    engine of grid_unittest.x / grid_miniapp.x) reads its own 13 sample .task files and
-    checks the batched legs of its unit test (src/grid/grid_unittest.c:51-57) against the
-    values stored in the files -- with this backend doing the work."""
-    import glob
+    engine of grid_unittest.x / grid_miniapp.x) reads the 13 sample tasks (regenerated in
+    its file format from tests/golden/*.npz) and checks the batched legs of its unit test
+    (src/grid/grid_unittest.c:51-57) against the values stored in the files -- with this
+    backend doing the work."""
     import subprocess
     import sys
 
     _pyref()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    if not glob.glob(os.path.join(root, "oracle", "_ref", "sample_tasks", "*.task")):
-        pytest.skip("oracle/_ref/sample_tasks not present (made by `make -C oracle ref_b200`)")
-    out = subprocess.run([sys.executable, "-c", _REPLAY_SCRIPT.format(root=root)], capture_output=True,
-                         text=True, timeout=600)
+    _write_sample_tasks(tmp_path)
+    out = subprocess.run([sys.executable, "-c", _REPLAY_SCRIPT.format(root=root, tasks=str(tmp_path))],
+                         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "REPLAY_DONE 13 []" in out.stdout, out.stdout[-3000:]
