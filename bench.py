@@ -269,6 +269,8 @@ def main():
     ap.add_argument("--decomp", default="blocks", choices=["blocks", "slab"],
                     help="multi-GPU decomposition: matrix blocks + replicated grids + all-reduce (default), "
                          "or z-slab rs_grids + NCCL halo sum/fill (cp2k_b200/rsgrid.py)")
+    ap.add_argument("--slab-compact", action="store_true",
+                    help="with --decomp slab: per-rank compacted P/H blocks + all-to-all owner reduction of H")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.forces = args.forces or args.virial
@@ -311,12 +313,16 @@ def main():
     lib.set_kernel_variant(args.variant)
 
     wl_full = build_h2o_workload(args.workload, basis=args.basis)
-    slab_levels = None
+    slab_levels, hab_exchange = None, None
     if args.decomp == "slab" and world > 1:
         from cp2k_b200 import rsgrid
 
         slab_levels = rsgrid.make_slab_levels(wl_full, world)
-        wl = rsgrid.local_workload(wl_full, slab_levels, rank, world)
+        wl = rsgrid.local_workload(wl_full, slab_levels, rank, world, compact_blocks=args.slab_compact)
+        # --slab-compact (opt-in; CPU-tested with gloo, not yet timed on GPUs): the rank's P/H
+        # buffers hold its own blocks only and the partial H blocks are summed into their
+        # owners with one all-to-all instead of an all-reduce of the whole H buffer
+        hab_exchange = rsgrid.HabExchange(wl_full, slab_levels, rank, world) if args.slab_compact else None
     else:
         wl = split_blocks(wl_full, world, rank)
     tl = wl.create(lib)
@@ -356,8 +362,11 @@ def main():
         tl.collocate(100, pab, grids)
         exchange(grids)
         tl.integrate(False, pab if args.forces else None, grids, hab, forces, virial)
-        if slab_levels is not None:
-            dist.all_reduce(hab.device)  # a block's tasks may live on several slabs
+        if slab_levels is not None:  # a block's tasks may live on several slabs
+            if hab_exchange is not None:
+                hab_exchange.reduce(hab.device[: wl.pab_len], dist)
+            else:
+                dist.all_reduce(hab.device)
 
     def barrier():
         if world > 1:
@@ -442,7 +451,10 @@ def main():
         exchange(grids)
         tl.integrate(False, pab if args.forces else None, grids, hab, forces, virial)
         if slab_levels is not None:
-            dist.all_reduce(hab.device)
+            if hab_exchange is not None:
+                hab_exchange.reduce(hab.device[: wl.pab_len], dist)
+            else:
+                dist.all_reduce(hab.device)
         pin_hab.copy_(hab.device[: wl.pab_len], non_blocking=True)
         torch.cuda.synchronize()
 

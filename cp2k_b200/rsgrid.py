@@ -91,15 +91,12 @@ def _exponents(wl: Workload, kinds, isets, ipgfs) -> np.ndarray:
     return out
 
 
-def local_workload(wl: Workload, levels: Sequence[SlabLevel], rank: int, world: int) -> Workload:
-    """The task list and grid layouts of one rank.
-
-    Distributed levels: a task belongs to the rank owning the z-plane of its cube
-    centre (the halo is wide enough for the whole cube).  Replicated levels: tasks
-    are dealt to ranks by matrix block (every rank holds the full grid)."""
+def task_owner(wl: Workload, levels: Sequence[SlabLevel], world: int) -> np.ndarray:
+    """Rank that works on every task.  Distributed levels: the rank owning the z-plane of
+    the task's cube centre (the halo is wide enough for the whole cube).  Replicated
+    levels: tasks are dealt to ranks by matrix block (every rank holds the full grid)."""
     t = wl.tasks
-    keep = np.zeros(wl.ntasks, dtype=bool)
-    layouts = []
+    owner = np.zeros(wl.ntasks, dtype=np.int32)
     for ilev, (lay, sl) in enumerate(zip(wl.layouts, levels)):
         sel = np.nonzero(t["level_list"] == ilev + 1)[0]
         if sl.distributed:
@@ -110,19 +107,87 @@ def local_workload(wl: Workload, levels: Sequence[SlabLevel], rank: int, world: 
             rp_z = wl.atom_positions[ia, 2] + zetb / (zeta + zetb) * t["rab_list"][sel, 2]
             nz = int(sl.npts_global[2])
             centre = np.floor(lay.dh_inv[2][2] * rp_z).astype(np.int64) % nz
+            bounds = np.array([hi for _, hi in sl.owned])
+            owner[sel] = np.searchsorted(bounds, centre, side="right")
+        else:
+            owner[sel] = (t["block_num_list"][sel] - 1) % world
+    return owner
+
+
+def local_workload(wl: Workload, levels: Sequence[SlabLevel], rank: int, world: int,
+                   compact_blocks: bool = False) -> Workload:
+    """The task list and grid layouts of one rank (see `task_owner`).  With
+    `compact_blocks` the rank's P/H buffers hold only the blocks its tasks refer to
+    (see `HabExchange` for summing the H blocks into their owners)."""
+    keep = task_owner(wl, levels, world) == rank
+    layouts = []
+    for lay, sl in zip(wl.layouts, levels):
+        if sl.distributed:
             lo, hi = sl.owned[rank]
-            keep[sel[(centre >= lo) & (centre < hi)]] = True
             nloc = np.array(lay.npts_global, dtype=np.int32)
             nloc[2] = (hi - lo) + 2 * sl.border
             shift = np.array([0, 0, lo - sl.border], dtype=np.int32)
             layouts.append(GridLayout(lay.npts_global, nloc, shift, np.array([0, 0, sl.border], np.int32),
                                       lay.dh, lay.dh_inv))
         else:
-            keep[sel[(t["block_num_list"][sel] - 1) % world == rank]] = True
             layouts.append(lay)
-    sub = wl.subset(keep)
+    sub = wl.subset(keep, compact_blocks=compact_blocks)
     sub.layouts = layouts
     return sub
+
+
+class HabExchange:
+    """Sums the ranks' partial H blocks into the blocks' owners -- the restatement of
+    rs_gather_matrices / rs_scatter_matrices' all-to-all (src/task_list_methods.F:2419-2667)
+    for ranks whose buffers hold only the blocks they touch (`compact_blocks=True`).
+
+    Matrix blocks are owned in contiguous ranges of (almost) equal size in doubles;
+    a rank's compacted buffer lists its blocks in ascending order, i.e. already grouped
+    by owner, so it IS the send buffer of one `all_to_all_single`; the receiver adds
+    every incoming segment into its owned slice through a precomputed index.  All
+    index arithmetic happens once, here."""
+
+    def __init__(self, wl: Workload, levels: Sequence[SlabLevel], rank: int, world: int):
+        sizes = np.diff(np.append(wl.block_offsets.astype(np.int64), wl.pab_len))
+        offsets = wl.block_offsets.astype(np.int64)
+        # contiguous ownership ranges balanced by size
+        bounds = np.searchsorted(np.cumsum(sizes), wl.pab_len * (np.arange(1, world) / world), side="left")
+        self.block_range = [(int(a), int(b)) for a, b in
+                            zip(np.concatenate([[0], bounds]), np.concatenate([bounds, [wl.nblocks]]))]
+        b_owner = np.zeros(wl.nblocks, dtype=np.int32)
+        for r, (a, b) in enumerate(self.block_range):
+            b_owner[a:b] = r
+        towner = task_owner(wl, levels, world)
+        used = [np.unique(wl.tasks["block_num_list"][towner == r] - 1) for r in range(world)]
+        lo, hi = self.block_range[rank]
+        self.owned_start = int(offsets[lo]) if lo < wl.nblocks else wl.pab_len
+        self.owned_len = int(sizes[lo:hi].sum())
+        self.in_split = [int(sizes[used[rank][b_owner[used[rank]] == o]].sum()) for o in range(world)]
+        self.out_split, idx = [], []
+        for src in range(world):
+            mine = used[src][b_owner[used[src]] == rank]
+            self.out_split.append(int(sizes[mine].sum()))
+            if mine.size:
+                idx.append(np.repeat(offsets[mine] - self.owned_start - np.concatenate(
+                    [[0], np.cumsum(sizes[mine])[:-1]]), sizes[mine]) + np.arange(int(sizes[mine].sum())))
+        self.recv_index = np.concatenate(idx).astype(np.int64) if idx else np.zeros(0, np.int64)
+        self._dev = {}
+
+    def reduce(self, my_hab, dist):
+        """`my_hab`: the rank's compacted H buffer (torch tensor).  Returns the summed H
+        of the blocks this rank owns, as a tensor of `owned_len` doubles (the slice
+        [owned_start, owned_start + owned_len) of the global block buffer)."""
+        import torch
+
+        assert my_hab.numel() == sum(self.in_split)
+        recv = torch.empty(sum(self.out_split), dtype=my_hab.dtype, device=my_hab.device)
+        dist.all_to_all_single(recv, my_hab.contiguous(), self.out_split, self.in_split)
+        key = str(my_hab.device)
+        if key not in self._dev:
+            self._dev[key] = torch.from_numpy(self.recv_index).to(my_hab.device)
+        out = torch.zeros(self.owned_len, dtype=my_hab.dtype, device=my_hab.device)
+        out.index_add_(0, self._dev[key], recv)
+        return out
 
 
 # ----------------------------------------------------------------------------

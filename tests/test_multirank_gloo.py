@@ -102,6 +102,22 @@ def _worker(rank, world, port, mode, result_file):
         dist.all_reduce(t)
         errs["hab"] = float(np.abs(hab.host - hab_full.host).max())
         tl.free()
+        # the same with per-rank compacted P/H blocks and the owner reduction (one all-to-all)
+        from cp2k_b200.workload import block_index_map
+        cmine = rsgrid.local_workload(wl, levels, rank, world, compact_blocks=True)
+        assert cmine.ntasks == mine.ntasks and cmine.pab_len <= wl.pab_len
+        tl = cmine.create(ora)
+        chab = OffloadBuffer(cmine.pab_len)
+        tl.integrate(False, None, grids, chab)
+        tl.free()
+        ex = rsgrid.HabExchange(wl, levels, rank, world)
+        assert np.array_equal(block_index_map(cmine).size, sum(ex.in_split))
+        own = ex.reduce(torch.from_numpy(chab.host), dist).numpy()
+        want = hab_full.host[ex.owned_start: ex.owned_start + ex.owned_len]
+        errs["hab"] = max(errs["hab"], float(np.abs(own - want).max()) if own.size else 0.0)
+        covered = torch.tensor([ex.owned_len], dtype=torch.int64)
+        dist.all_reduce(covered)
+        assert int(covered) == wl.pab_len  # the owned slices tile the whole block buffer
     if rank == 0:
         np.save(result_file, np.array([errs["grid"], errs["hab"]]))
     dist.barrier()
