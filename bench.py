@@ -150,11 +150,70 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(wl, args, extra={"sample": res["sample"]}),
         "cpu_baseline": {"value": res["value"], "unit": "GFLOP/s", "cores": res["cores"], "kind": "reference",
-                         "sample": res["sample"]},
+                         "sample": res["sample"], "same_config": res["same_config"],
+                         "dgemm_shim_share": res["dgemm_shim_share"]},
         "e2e": {"value": res["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def reference_gpu_timing(wl, steps, warmup, forces, virial=False, device=0):
+    """Times the UNMODIFIED reference CUDA backend (src/grid/gpu compiled for sm_100a,
+    oracle/_ref/libgrid_ref_gpu.so) through the reference's public API on the same task list.
+    Its API is synchronous and always moves P/H blocks and grids between the caller's pinned
+    host buffers and its device buffers (gpu/grid_gpu_context.cu:479-655), so the number is an
+    END-TO-END one: compare with our `e2e`, not with the resident `value`."""
+    from cp2k_b200.grid_api import OffloadBuffer
+    from oracle import pyref
+
+    lib = pyref.load_reference_gpu(device)
+    t0 = time.perf_counter()
+    tl = wl.create(lib)
+    create_s = time.perf_counter() - t0
+    pab = wl.random_pab(1, make=OffloadBuffer.with_device)
+    grids = wl.new_grids(make=OffloadBuffer.with_device)
+    hab = OffloadBuffer.with_device(wl.pab_len)
+    f = np.zeros((wl.natoms, 3)) if forces else None
+    v = np.zeros((3, 3)) if virial else None
+    times, tc, ti = [], [], []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        tl.collocate(100, pab, grids)
+        t1 = time.perf_counter()
+        tl.integrate(False, pab if forces else None, grids, hab, f, v)
+        t2 = time.perf_counter()
+        if i >= warmup:
+            times.append(t2 - t0), tc.append(t1 - t0), ti.append(t2 - t1)
+    tl.free()
+    return {"ms_per_step": float(np.mean(times)) * 1e3, "collocate_ms": float(np.mean(tc)) * 1e3,
+            "integrate_ms": float(np.mean(ti)) * 1e3, "create_task_list_s": create_s, "steps": steps,
+            "what": "reference CUDA backend (src/grid/gpu, sm_100a build), public API, pinned host buffers in/out"}
+
+
+def run_reference_gpu(args):
+    import torch
+
+    from cp2k_b200.workload import build_h2o_workload
+    from oracle import pyref
+
+    if not pyref.have_reference_gpu() or not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "oracle/_ref/libgrid_ref_gpu.so not built or no GPU"}))
+        return
+    wl = build_h2o_workload(args.workload, basis=args.basis)
+    res = reference_gpu_timing(wl, args.steps, max(args.warmup, 1), args.forces, args.virial)
+    ora = pyref.load_oracle()
+    flops = model_flops_cpu(wl, ora)
+    val = flops / (res["ms_per_step"] * 1e-3) * 1e-9
+    grid_bytes = 8 * sum(l.npts_local_total for l in wl.layouts)
+    print(json.dumps({
+        "impl": "reference-gpu", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(wl, args), "detail": res,
+        "e2e": {"value": val, "unit": "GFLOP/s", "ms_per_step": res["ms_per_step"],
+                "h2d_bytes_per_step": 8 * wl.pab_len + grid_bytes, "d2h_bytes_per_step": 8 * wl.pab_len + grid_bytes},
+    }))
 
 
 METRIC = "grid collocate+integrate model FP64 GFLOP/s per SCF step (s/SCF-step = ms_per_step/1000)"
@@ -224,10 +283,20 @@ def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0, virial=False)
         stride = int(np.ceil(1.0 / frac))
         sample = wl.subset(((wl.tasks["block_num_list"] - 1) % stride) == 0)
         desc = f"every {stride}-th matrix block ({sample.ntasks} of {wl.ntasks} tasks), full-size grids"
+    shim = getattr(lib.lib, "ref_shims_dgemm_stats", None)
+    sec, calls = ctypes.c_double(0.0), ctypes.c_longlong(0)
+    if shim is not None:
+        shim.restype = None
+        shim(ctypes.byref(sec), ctypes.byref(calls), 1)  # reset
     t_step = one(sample, steps, warmup)
+    dgemm_share = None
+    if shim is not None:  # thread-seconds inside the link shim over thread-seconds of the timed + warm-up steps
+        shim(ctypes.byref(sec), ctypes.byref(calls), 1)
+        dgemm_share = float(sec.value) / max(t_step * (steps + warmup) * cores, 1e-12)
     flops = model_flops_cpu(sample, ora)
     return {"value": flops / t_step * 1e-9, "ms_per_step": t_step * 1e3, "cores": cores, "sample": desc,
-            "sample_fraction": sample.ntasks / wl.ntasks}
+            "sample_fraction": sample.ntasks / wl.ntasks, "same_config": sample is wl,
+            "dgemm_shim_share": dgemm_share}
 
 
 def model_flops_cpu(wl, ora):
@@ -257,13 +326,19 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"],
+                    help="reference = the reference's CPU backend on the host cores (the contract's reference arm); "
+                         "reference-gpu = the reference's own CUDA backend compiled for sm_100a (SURVEY 8(a) a19)")
     ap.add_argument("--workload", default="H2O-256")
     ap.add_argument("--basis", default="TZV2P-GTH", choices=["TZV2P-GTH", "DZVP-MOLOPT-SR-GTH"],
                     help="TZV2P-GTH as shipped in benchmarks/QS/H2O-N.inp; DZVP-MOLOPT-SR-GTH is BASELINE config 2's")
     ap.add_argument("--forces", action="store_true", help="integrate with forces (BASELINE config 3)")
     ap.add_argument("--virial", action="store_true", help="... and the virial (implies --forces)")
-    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--cpu-budget", type=float, default=600.0,
+                    help="seconds the CPU reference may take over all its steps before its task list is thinned "
+                         "(the default covers the full H2O-256 / H2O-1024 lists: same config as the GPU arm)")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the reference-CUDA-backend leg of the N=1 line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--decomp", default="blocks", choices=["blocks", "slab"],
@@ -282,6 +357,10 @@ def main():
     if args.impl == "reference":
         if rank == 0:
             run_reference(args)
+        return
+    if args.impl == "reference-gpu":
+        if rank == 0:
+            run_reference_gpu(args)
         return
 
     import torch
@@ -484,8 +563,20 @@ def main():
         if pyref.have_reference():
             r = cpu_reference_timing(wl_full, 2, 1, args.forces, budget_s=args.cpu_budget, virial=args.virial)
             cpu_baseline = {"value": r["value"], "unit": "GFLOP/s", "cores": r["cores"], "kind": "reference",
-                            "sample": r["sample"], "ms_per_step_sample": r["ms_per_step"],
-                            "ms_per_step_extrapolated": r["ms_per_step"] / r["sample_fraction"]}
+                            "sample": r["sample"], "same_config": r["same_config"],
+                            "ms_per_step_sample": r["ms_per_step"],
+                            "ms_per_step_extrapolated": r["ms_per_step"] / r["sample_fraction"],
+                            "dgemm_shim_share": r["dgemm_shim_share"]}
+
+    reference_gpu = None
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        from oracle import pyref
+
+        if pyref.have_reference_gpu():
+            tl.free()
+            tl = None
+            torch.cuda.empty_cache()
+            reference_gpu = reference_gpu_timing(wl_full, 3, 1, args.forces, args.virial, device=local_rank)
 
     if rank == 0:
         line = {
@@ -502,10 +593,11 @@ def main():
             "e2e": {"value": flops_total / (e2e_ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu,
         }
         print(json.dumps(line))
-    tl.free()
+    if tl is not None:
+        tl.free()
     if world > 1:
         dist.destroy_process_group()
 

@@ -156,7 +156,7 @@ struct TiledLevel {
 // with kbase = offset_n + (nby + kKPad - oy) * kKPitch + (nbx + kKPad - ox).
 // ---------------------------------------------------------------------------
 inline void build_ktabs(const LevelDev &L, const int max_n, std::vector<KTabHeader> &heads,
-                        std::vector<unsigned char> &tab) {
+                        std::vector<unsigned char> &tab, const int pitch = kKPitch, const int pad = kKPad) {
   const double h[3] = {L.dh[0], L.dh[4], L.dh[8]};
   const double hinv[3] = {L.dh_inv[0], L.dh_inv[4], L.dh_inv[8]};
   const double drmin = fmin(h[0], fmin(h[1], h[2]));
@@ -187,17 +187,17 @@ inline void build_ktabs(const LevelDev &L, const int max_n, std::vector<KTabHead
       }
     }
     H.offset = (int)tab.size();
-    const int rows = 2 * nb[1] + 2 * kKPad + 1;
-    tab.resize(tab.size() + (size_t)rows * kKPitch, (unsigned char)0);
+    const int rows = 2 * nb[1] + 2 * pad + 1;
+    tab.resize(tab.size() + (size_t)rows * pitch, (unsigned char)0);
     for (int dj = -nb[1]; dj <= nb[1] + 1; dj++)
       for (int di = -nb[0]; di <= nb[0] + 1; di++) {
         const int mj = (dj <= 0) ? -dj : dj - 1, mi = (di <= 0) ? -di : di - 1;
-        tab[(size_t)H.offset + (size_t)(dj + nb[1] + kKPad) * kKPitch + (di + nb[0] + kKPad)] =
+        tab[(size_t)H.offset + (size_t)(dj + nb[1] + pad) * pitch + (di + nb[0] + pad)] =
             (unsigned char)(K[(size_t)mj * px + mi] + 1);
       }
     heads[n] = H;
   }
-  tab.resize((tab.size() + 15) / 16 * 16 + 16 * kKPitch, (unsigned char)0);  // slack for the +4 rows of column 1
+  tab.resize((tab.size() + 15) / 16 * 16 + 16 * pitch, (unsigned char)0);  // slack for the +4 rows of column 1
 }
 
 // zmask[K1][oz + kZmBias]: bit p set <=> plane p of the block lies within
@@ -633,6 +633,30 @@ template <int N> struct WarpVecReduce {
 template <int N> struct DupLanes {
   static constexpr int splits = (N > 16) ? 5 : (N > 8 ? 4 : (N > 4 ? 3 : (N > 2 ? 2 : (N > 1 ? 1 : 0))));
   static constexpr int value = 32 >> splits;
+};
+
+// Lanes that hold a REAL element after WarpVecReduce<N> (bit L set <=> lane L's
+// (idx, v[0]) is element idx of the vector, not the zero padding of an odd split).
+// A padded lane can carry an idx < N that belongs to another lane's element: harmless
+// for atomic adds of its zero, fatal for plain stores -- those must test this mask.
+template <int N> struct ValidLanes {
+  static constexpr unsigned compute() {
+    unsigned mask = 0u;
+    for (int lane = 0; lane < 32; lane++) {
+      int m = N, cnt = N;
+      for (int off = 16; off >= 1; off /= 2) {
+        if (m > 1) {
+          const int h = (m + 1) / 2;
+          cnt = (lane & off) ? (cnt - h > 0 ? cnt - h : 0) : (cnt < h ? cnt : h);
+          m = h;
+        }
+      }
+      if (cnt >= 1)
+        mask |= 1u << lane;
+    }
+    return mask;
+  }
+  static constexpr unsigned value = compute();
 };
 
 // Integrate epilogue of one (pair, warp): every thread holds the z-contracted
@@ -1072,7 +1096,7 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
     }
     A.tt_first = tl.class_tt_first[cls];
     A.coef_base = tl.coef_base[L.dl][cls];
-    A.coef_stride = ncoset(hi);
+    A.coef_stride = (ncoset(hi) + 1) / 2 * 2;  // slots are padded to even sizes (ensure_coef_offsets)
     cudaStream_t s = L.stream;
     if (per_lp && lo == 0) {  // the dominant class only (water: lp 0..2)
       int *const counter0 = A.counter;

@@ -22,6 +22,7 @@
 #include "b200_coef.cuh"
 #include "b200_generic.cuh"
 #include "b200_tiled.cuh"
+#include "b200_ctile.cuh"
 
 namespace b200 {
 
@@ -32,7 +33,14 @@ static std::atomic<long long> g_launches{0};
 static int g_device = -1;
 static cudaStream_t g_stream = nullptr;
 static bool g_device_resident = false;
+// kernel family: 0 = automatic (kDefaultPath), 1 = generic kernels only, 2 = warp-tile kernels
+// (b200_tiled.cuh), 3 = CTA-tile kernels (b200_ctile.cuh)
 static int g_variant = 0;
+constexpr int kDefaultPath = 2;  // what "automatic" resolves to: the faster family on the H2O benchmarks
+static inline int variant_path() {
+  const int v = (g_variant == 0) ? kDefaultPath : g_variant;
+  return v == 3 ? 0 : 2;  // TaskList::path: 0 = CTA-tile data, 2 = warp-tile data
+}
 static bool g_tables_uploaded[64] = {false};
 
 void count_launch(int n) { g_launches += n; }
@@ -134,7 +142,8 @@ struct LevelInfo {
   int max_lp0 = 0;                   // max la_max+lb_max over the level
   int max_w = 1;                     // max cube / index-box edge
   int max_lp0_general = -1;          // over non-ortho tasks
-  TiledLevel tiled;                  // tiled-path data (b200_tiled.cuh)
+  TiledLevel tiled;                  // warp-tile path data (b200_tiled.cuh), path == 2
+  CtileLevel ctile;                  // CTA-tile path data (b200_ctile.cuh), path == 0
 };
 
 constexpr int kNumSizeClasses = 3;
@@ -201,6 +210,8 @@ struct TaskList {
   std::vector<cudaEvent_t> ev_join;
   double stats[16] = {0};
   bool stats_ready = false;
+  int path = 0;                      // which tiled family the list was built for (0 / 2)
+  CtileList ct;
 
   void release() {
     for (auto st : level_streams)
@@ -245,7 +256,8 @@ struct TaskList {
     h_glists.clear();
     d_glists.release();
     for (auto &li : linfo)
-      li.tiled.release();
+      li.tiled.release(), li.ctile.release();
+    ct.release();
     for (int i = 0; i < 8; i++)
       coef_ready[i] = false, coef_total[i] = 0;
     stats_ready = false;
@@ -396,16 +408,21 @@ static void ensure_coef_offsets(TaskList &tl, int dl, cudaStream_t s) {
     return;
   std::vector<int> off(tl.ntasks, -1);
   size_t total = 0;
+  // (slots start at even offsets and have even strides: 16-byte aligned for the bulk copies)
   for (int lev = 0; lev < tl.nlevels; lev++) {
-    TiledLevel &T = tl.linfo[lev].tiled;
+    LevelInfo &li = tl.linfo[lev];
+    const bool ct = (tl.path == 0);
+    const int ntiled = ct ? li.ctile.ntasks_tiled : li.tiled.ntasks_tiled;
+    const int *tt_first = ct ? li.ctile.class_tt_first : li.tiled.class_tt_first;
+    const std::vector<int> &tt_task = ct ? li.ctile.h_tt_task : li.tiled.h_tt_task;
     for (int cls = 0; cls < kNumClasses; cls++) {
-      const int stride = ncoset(kClassHi[cls] + dl);
+      const int stride = (ncoset(kClassHi[cls] + dl) + 1) / 2 * 2;
       B200_ASSERT(total < (size_t)INT_MAX, "coefficient buffer exceeds 2^31 entries");
-      T.coef_base[dl][cls] = (int)total;
-      if (T.ntasks_tiled == 0)
+      (ct ? li.ctile.coef_base : li.tiled.coef_base)[dl][cls] = (int)total;
+      if (ntiled == 0)
         continue;
-      for (int q = T.class_tt_first[cls]; q < T.class_tt_first[cls + 1]; q++) {
-        off[T.h_tt_task[q]] = (int)total;
+      for (int q = tt_first[cls]; q < tt_first[cls + 1]; q++) {
+        off[tt_task[q]] = (int)total;
         total += stride;
       }
     }
@@ -413,7 +430,7 @@ static void ensure_coef_offsets(TaskList &tl, int dl, cudaStream_t s) {
   for (int i = 0; i < tl.ntasks; i++)
     if (off[i] < 0) {
       off[i] = (int)total;
-      total += ncoset(tl.h_tasks[i].la_max + tl.h_tasks[i].lb_max + dl);
+      total += (ncoset(tl.h_tasks[i].la_max + tl.h_tasks[i].lb_max + dl) + 1) / 2 * 2;
     }
   total += 256;  // slack for whole-slot prefetches
   B200_ASSERT(total < (size_t)INT_MAX, "coefficient buffer exceeds 2^31 entries");
@@ -435,6 +452,7 @@ static void build_task_list(
     const int *npts_global, const int *npts_local, const int *shift_local,
     const int *border_width, const double *dh, const double *dh_inv) {
   cudaStream_t s = g_stream;
+  tl.path = (nlevels > kCtMaxLevels) ? 2 : variant_path();
   tl.ortho = orthorhombic;
   tl.ntasks = ntasks, tl.nlevels = nlevels, tl.natoms = natoms;
   tl.nkinds = nkinds, tl.nblocks = nblocks;
@@ -696,13 +714,22 @@ static void build_task_list(
   for (int l = 0; l < nlevels; l++) {
     LevelInfo &li = tl.linfo[l];
     std::vector<int> generic_ids;
-    build_tiled_level(li.tiled, tl.levels[l], tl.h_tasks, tl.d_tasks.p, li.first, li.last, generic_ids, s);
+    if (tl.path == 0)
+      build_ctile_level(li.ctile, l, tl.levels[l], tl.h_tasks, li.first, li.last, generic_ids, s);
+    else
+      build_tiled_level(li.tiled, tl.levels[l], tl.h_tasks, tl.d_tasks.p, li.first, li.last, generic_ids, s);
     li.n_generic = (int)generic_ids.size();
     tl.generic_first[l] = (int)tl.h_generic_ids.size();
     tl.h_generic_ids.insert(tl.h_generic_ids.end(), generic_ids.begin(), generic_ids.end());
   }
   tl.generic_first[nlevels] = (int)tl.h_generic_ids.size();
   tl.d_generic_ids.upload(tl.h_generic_ids, s);
+  if (tl.path == 0) {
+    std::vector<CtileLevel *> cls;
+    for (int l = 0; l < nlevels; l++)
+      cls.push_back(&tl.linfo[l].ctile);
+    finish_ctile_list(tl.ct, cls, s);
+  }
   tl.level_streams.resize(nlevels);
   tl.ev_join.resize(nlevels);
   B200_CHECK(cudaEventCreateWithFlags(&tl.ev_fork, cudaEventDisableTiming));
@@ -895,9 +922,63 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
     }
   }
 
+  if (tl.path == 0 && g_variant != 1) {
+    // CTA-tile path: one launch per lp class covers all levels (the work items of the
+    // small levels fill the tail of the big one); generic leftovers follow per level.
+    ScopedTimer *tm_grid = new ScopedTimer(T_COLLOCATE, s);
+    std::vector<double *> dg(nlevels);
+    std::vector<CtileLevel *> cl(nlevels);
+    bool any_host = false;
+    for (int l = 0; l < nlevels; l++) {
+      const LevelDev &L = tl.levels[l];
+      const size_t npts = (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2];
+      B200_ASSERT(grids[l]->size >= npts * sizeof(double), "grid buffer smaller than npts_local");
+      double *d_grid = use_caller_device(grids[l]) ? grids[l]->device_buffer : nullptr;
+      if (d_grid == nullptr) {
+        tl.d_grids[l].ensure(npts);
+        d_grid = tl.d_grids[l].p;
+      }
+      dg[l] = d_grid, cl[l] = &tl.linfo[l].ctile;
+      B200_CHECK(cudaMemsetAsync(d_grid, 0, npts * sizeof(double), s));
+    }
+    CtileCall C;
+    C.list = &tl.ct, C.levels = cl.data(), C.level_dev = tl.levels.data(), C.grids = dg.data();
+    C.l0 = 0, C.l1 = nlevels, C.dl = dl, C.coef = tl.d_coef.p, C.stream = s;
+    const unsigned leftover = launch_ctile<true>(C);
+    for (int l = 0; l < nlevels; l++) {
+      LevelInfo &li = tl.linfo[l];
+      GridLaunch GL;
+      GL.tasks = tl.d_tasks.p, GL.level = tl.levels[l], GL.dl = dl;
+      GL.coef_offsets = tl.d_coef_off[dl].p, GL.coef = tl.d_coef.p, GL.grid = dg[l];
+      GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = s;
+      GL.task_ids = tl.d_generic_ids.p + tl.generic_first[l], GL.ntasks = li.n_generic;
+      launch_generic(GL, true);
+      for (int cls = 0; cls < kNumClasses; cls++)
+        if (leftover & (1u << cls)) {
+          GL.task_ids = li.ctile.d_class_task_ids[cls], GL.ntasks = li.ctile.class_ntasks[cls];
+          launch_generic(GL, true);
+        }
+    }
+    delete tm_grid;
+    for (int l = 0; l < nlevels; l++) {
+      const bool resident = g_device_resident && use_caller_device(grids[l]);
+      if (!resident) {
+        const LevelDev &L = tl.levels[l];
+        const size_t npts = (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2];
+        ScopedTimer tm(T_D2H, s);
+        B200_CHECK(cudaMemcpyAsync(grids[l]->host_buffer, dg[l], npts * sizeof(double), cudaMemcpyDeviceToHost, s));
+        any_host = true;
+      }
+    }
+    if (!g_device_resident || any_host)
+      B200_CHECK(cudaStreamSynchronize(s));
+    return;
+  }
+
   // The levels are independent: fork one stream per level, join afterwards.
   // T_COLLOCATE spans fork..join, i.e. all grid kernels of this call.
   ScopedTimer *tm_grid = new ScopedTimer(T_COLLOCATE, s);
+  bool any_host_copy = false;
   B200_CHECK(cudaEventRecord(tl.ev_fork, s));
   for (int l = 0; l < nlevels; l++) {
     const LevelDev &L = tl.levels[l];
@@ -933,15 +1014,19 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
           }
       }
     }
-    if (!resident)
+    if (!resident) {
       B200_CHECK(cudaMemcpyAsync(grids[l]->host_buffer, d_grid, npts * sizeof(double),
                                  cudaMemcpyDeviceToHost, ls));
+      any_host_copy = true;
+    }
     B200_CHECK(cudaEventRecord(tl.ev_join[l], ls));
   }
   for (int l = 0; l < nlevels; l++)
     B200_CHECK(cudaStreamWaitEvent(s, tl.ev_join[l], 0));
   delete tm_grid;
-  if (!g_device_resident)
+  // host_buffer is the source of truth for every buffer that was not resident: the
+  // copies back must have landed when the call returns
+  if (!g_device_resident || any_host_copy)
     B200_CHECK(cudaStreamSynchronize(s));
 }
 
@@ -991,6 +1076,44 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
     B200_CHECK(cudaMemsetAsync(tl.d_coef.p, 0, tl.coef_total[dl] * sizeof(double), s));
   }
 
+  if (tl.path == 0 && g_variant != 1) {
+    std::vector<double *> dg(nlevels);
+    std::vector<CtileLevel *> cl(nlevels);
+    for (int l = 0; l < nlevels; l++) {
+      const LevelDev &L = tl.levels[l];
+      const size_t npts = (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2];
+      B200_ASSERT(grids[l]->size >= npts * sizeof(double), "grid buffer smaller than npts_local");
+      double *d_grid = use_caller_device(grids[l]) ? grids[l]->device_buffer : nullptr;
+      if (!(g_device_resident && d_grid != nullptr)) {
+        if (d_grid == nullptr) {
+          tl.d_grids[l].ensure(npts);
+          d_grid = tl.d_grids[l].p;
+        }
+        ScopedTimer tm(T_H2D, s);
+        B200_CHECK(cudaMemcpyAsync(d_grid, grids[l]->host_buffer, npts * sizeof(double), cudaMemcpyHostToDevice, s));
+      }
+      dg[l] = d_grid, cl[l] = &tl.linfo[l].ctile;
+    }
+    ScopedTimer tm_g(T_INTEGRATE, s);
+    CtileCall C;
+    C.list = &tl.ct, C.levels = cl.data(), C.level_dev = tl.levels.data(), C.grids = dg.data();
+    C.l0 = 0, C.l1 = nlevels, C.dl = dl, C.coef = tl.d_coef.p, C.stream = s;
+    const unsigned leftover = launch_ctile<false>(C);
+    for (int l = 0; l < nlevels; l++) {
+      LevelInfo &li = tl.linfo[l];
+      GridLaunch GL;
+      GL.tasks = tl.d_tasks.p, GL.level = tl.levels[l], GL.dl = dl;
+      GL.coef_offsets = tl.d_coef_off[dl].p, GL.coef = tl.d_coef.p, GL.grid = dg[l];
+      GL.max_lp = li.max_lp0 + dl, GL.max_w = li.max_w, GL.stream = s;
+      GL.task_ids = tl.d_generic_ids.p + tl.generic_first[l], GL.ntasks = li.n_generic;
+      launch_generic(GL, false);
+      for (int cls = 0; cls < kNumClasses; cls++)
+        if (leftover & (1u << cls)) {
+          GL.task_ids = li.ctile.d_class_task_ids[cls], GL.ntasks = li.ctile.class_ntasks[cls];
+          launch_generic(GL, false);
+        }
+    }
+  } else {
   ScopedTimer *tm_grid = new ScopedTimer(T_INTEGRATE, s);
   B200_CHECK(cudaEventRecord(tl.ev_fork, s));
   // Host-authoritative grids are uploaded coarsest level first: its kernels start after a
@@ -1039,6 +1162,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   for (int l = 0; l < nlevels; l++)
     B200_CHECK(cudaStreamWaitEvent(s, tl.ev_join[l], 0));
   delete tm_grid;
+  }
 
   const double *d_pab = nullptr;
   if (do_f) {
@@ -1116,7 +1240,8 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   if (do_v)
     B200_CHECK(cudaMemcpyAsync(virial, tl.d_fv.p + (size_t)3 * natoms, sizeof(double) * 9,
                                cudaMemcpyDeviceToHost, s));
-  if (!g_device_resident || do_f || do_v)
+  // (hab not resident: its copy back to host_buffer must have landed on return)
+  if (!g_device_resident || !hab_resident || do_f || do_v)
     B200_CHECK(cudaStreamSynchronize(s));
 }
 
@@ -1133,7 +1258,7 @@ int grid_b200_get_stats(const grid_b200_task_list *ptr, double *out, const int n
       max_lp = std::max(max_lp, tl.linfo[l].max_lp0);
       max_w = std::max(max_w, tl.linfo[l].max_w);
       n_generic += tl.linfo[l].n_generic;
-      npairs += (double)tl.linfo[l].tiled.npairs;
+      npairs += (double)(tl.path == 0 ? tl.linfo[l].ctile.nvisits : tl.linfo[l].tiled.npairs);
     }
     tl.stats[0] = tl.ntasks, tl.stats[1] = tl.ntasks - n_generic, tl.stats[2] = n_generic;
     tl.stats[3] = npairs, tl.stats[7] = max_lp, tl.stats[8] = max_w / 2;

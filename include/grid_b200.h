@@ -170,8 +170,11 @@ void grid_b200_set_stream(void *cuda_stream);
  * false (default): host_buffer is authoritative; copies are part of the call. */
 void grid_b200_set_device_resident(const bool flag);
 
-/* 0 = automatic (tiled kernels where applicable), 1 = force the generic
- * per-task kernels everywhere (used by the parity tests to cover both). */
+/* Kernel family for orthorhombic tasks (the generic per-task kernels always cover what a
+ * tiled family cannot): 0 = automatic, 1 = generic kernels everywhere, 2 = warp-tile kernels,
+ * 3 = CTA-tile kernels (producer / consumer warps, bulk-async staging).  The family is fixed
+ * when a task list is created; 1 can be switched per call.  Used by the parity tests to
+ * cover all three. */
 void grid_b200_set_kernel_variant(const int variant);
 
 /* Number of CUDA kernels launched by this library since load. */

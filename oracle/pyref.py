@@ -17,8 +17,8 @@ import subprocess
 
 import numpy as np
 
-from cp2k_b200.grid_api import (GRID_BACKEND_CPU, GRID_BACKEND_REF, GridLibrary, _COffloadBuffer,
-                                _dptr, _iptr, _i32, _ip, _dp)
+from cp2k_b200.grid_api import (GRID_BACKEND_CPU, GRID_BACKEND_GPU, GRID_BACKEND_REF, GridLibrary,
+                                _COffloadBuffer, _dptr, _iptr, _i32, _ip, _dp)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libgrid_oracle.so")
@@ -27,6 +27,10 @@ REF_SO = os.path.join(HERE, "_ref", "libgrid_ref.so")
 # its public API reaches the product library as GRID_BACKEND_B200
 REF_B200_SO = os.path.join(HERE, "_ref", "libgrid_ref_b200.so")
 GRID_BACKEND_B200 = 15
+# the same unmodified reference library built WITH its own CUDA backend (src/grid/gpu, -D__OFFLOAD_CUDA,
+# sm_100a): the comparator of SURVEY.md 8(a) row a19.  Needs a GPU to run; its offload_buffers must carry
+# pinned host memory and a device buffer (cp2k_b200.grid_api.OffloadBuffer(pinned=True, device=...)).
+REF_GPU_SO = os.path.join(HERE, "_ref", "libgrid_ref_gpu.so")
 
 
 def build(quiet: bool = True) -> None:
@@ -95,7 +99,8 @@ class ReferenceLibrary(GridLibrary):
         after every call (1e-12 on grids and hab, 1e-8 on forces/virial; it aborts on a
         mismatch, src/grid/grid_task_list.c:225-260, 352-420)."""
         assert backend in (GRID_BACKEND_REF, GRID_BACKEND_CPU) or \
-            (backend == GRID_BACKEND_B200 and self.path == REF_B200_SO)
+            (backend == GRID_BACKEND_B200 and self.path == REF_B200_SO) or \
+            (backend == GRID_BACKEND_GPU and self.path == REF_GPU_SO)
         self.backend = backend
         self.lib.grid_library_set_config(backend, bool(validate), False)
 
@@ -136,6 +141,24 @@ def load_reference_b200(validate: bool = True) -> ReferenceLibrary:
         _REFS["b200"] = ReferenceLibrary(GRID_BACKEND_B200, REF_B200_SO)
     lib = _REFS["b200"]
     lib.set_backend(GRID_BACKEND_B200, validate)
+    return lib
+
+
+def have_reference_gpu() -> bool:
+    return os.path.exists(REF_GPU_SO)
+
+
+def load_reference_gpu(device: int = 0, backend: int = GRID_BACKEND_GPU) -> ReferenceLibrary:
+    """The reference built with its CUDA backend; `device` is what CP2K's
+    offload_set_chosen_device would receive (src/offload/offload_library.c:88)."""
+    if "gpu" not in _REFS:
+        lib = ReferenceLibrary(backend, REF_GPU_SO)
+        lib.lib.offload_set_chosen_device.restype = None
+        lib.lib.offload_set_chosen_device.argtypes = [C.c_int]
+        _REFS["gpu"] = lib
+    lib = _REFS["gpu"]
+    lib.lib.offload_set_chosen_device(int(device))
+    lib.set_backend(backend)
     return lib
 
 

@@ -15,10 +15,10 @@ from synth import make_workload
 pytestmark = pytest.mark.gpu
 
 GRID_TOL, HAB_TOL, FV_TOL = 1e-10, 1e-10, 1e-8
-VARIANTS = [0, 1]  # 0 = automatic (tiled where applicable), 1 = generic kernels only
+VARIANTS = [3, 2, 1]  # 3 = CTA-tile kernels, 2 = warp-tile kernels (both with generic fallback), 1 = generic only
 
 
-@pytest.fixture(params=VARIANTS, ids=["auto", "generic"])
+@pytest.fixture(params=VARIANTS, ids=["ctile", "warptile", "generic"])
 def lib(b200, request):
     b200.set_kernel_variant(request.param)
     yield b200
