@@ -53,8 +53,9 @@ struct alignas(16) CWork {  // 32 bytes
   int b[4];                 // visit ranges per lp of the class: [b[i], b[i+1])
 };
 
-struct alignas(32) CVisit {  // one (task, tile) visit, see visitgen_kernel
+struct alignas(64) CVisit {  // one (task, tile) visit, see visitgen_kernel
   uint4 a, b;
+  CTask t;  // the task's data inlined: the producers stream the visit list, they never gather
 };
 
 struct CtileLevel {
@@ -108,12 +109,14 @@ inline std::vector<unsigned> build_ct_zmask() {
 //   a.y  sphere-table index of tile column (0, 0)
 //   a.z  cube centre relative to the tile origin: x | y << 8 | z << 16 (signed bytes)
 //   b.x, b.y  per warp block one byte: first | last << 4 plane any of its columns needs
+//   t    the task's sub-grid offset and exponent (a copy: the record is self-contained)
 // Which warp blocks a visit touches and their plane ranges are decided HERE, once per
 // task list, with the same exact test the round-1 pair generation used (the sphere
 // meets a block iff its column nearest to the centre reaches its nearest plane).
 // ---------------------------------------------------------------------------
 struct VisitGenArgs {
   const TTask *ttasks;
+  const CTask *ctasks;
   int nttasks;
   int nx, ny, nz, Nx, Ny, Nz;  // local / global grid size
   int ntx, nty, ntz;           // tiles per axis
@@ -182,20 +185,30 @@ template <int PASS> __global__ void visitgen_kernel(const VisitGenArgs A) {
               if (act == 0u)
                 continue;
               const unsigned tile = (unsigned)((tz * nt[1] + ty) * nt[0] + tx);
+              const int ox = cx - tx * B[0], oy = cy - ty * B[1], oz = cz - tz * B[2];
               const unsigned bucket = ((unsigned)lp_class(X.lp0) * A.ntiles + tile) * kLpBuckets + X.lp0;
               if (PASS == 0) {
                 atomicAdd(&A.bucket_count[bucket], 1u);
               } else {
                 const unsigned pos = A.bucket_start[bucket] + atomicAdd(&A.bucket_cursor[bucket], 1u);
-                const int ox = cx - tx * B[0], oy = cy - ty * B[1], oz = cz - tz * B[2];
                 CVisit V;
                 V.a.x = (unsigned)q | (act << 24);
                 V.a.y = (unsigned)(H.offset + (X.nb[1] + kCtKPad - oy) * kCtKPitch + (X.nb[0] + kCtKPad - ox));
                 V.a.z = ((unsigned)ox & 0xffu) | (((unsigned)oy & 0xffu) << 8) | (((unsigned)oz & 0xffu) << 16);
                 V.a.w = 0u;
                 V.b = make_uint4(wr[0], wr[1], 0u, 0u);
+                V.t = A.ctasks[q];
                 A.visits[pos] = V;
-                A.keys[pos] = ((unsigned long long)bucket << A.qbits) | (unsigned long long)q;
+                // Order inside a bucket: NOT by task.  Consecutive tasks (the pgf pairs of one atom
+                // pair share their centre) hit the same few warp blocks, and the slot ring only
+                // decouples the eight consumer warps by its depth: in task order a CTA runs on two
+                // or three warps at a time (measured: 17.7 ms per H2O-256 collocate against 12.7 ms
+                // with this order; dealing the visits round-robin by the warp block nearest to the
+                // centre instead was worse, 14.8 ms).  A bijective hash of the task index spreads
+                // every warp block's visits evenly over the list.  The order is still a pure
+                // function of the task list: results stay reproducible.
+                const unsigned long long hq = ((unsigned long long)q * 0x9E3779B1ull) & ((1ull << A.qbits) - 1ull);
+                A.keys[pos] = ((unsigned long long)bucket << A.qbits) | hq;
               }
             }
           }
@@ -209,7 +222,8 @@ template <int PASS> __global__ void visitgen_kernel(const VisitGenArgs A) {
 // Host: per-level build (task selection is the tiled path's: same criteria).
 // ---------------------------------------------------------------------------
 inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L, const std::vector<TaskDev> &tasks,
-                              const int first, const int last, std::vector<int> &generic_ids, cudaStream_t s) {
+                              const int first, const int last, std::vector<int> &generic_ids, const int item_cap,
+                              cudaStream_t s) {
   cl.release();
   const double h[3] = {L.dh[0], L.dh[4], L.dh[8]};
   const double drmin = fmin(h[0], fmin(h[1], h[2]));
@@ -288,14 +302,14 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
   up(&cl.d_khead, heads);
   up(&cl.d_ktab, ktab);
 
-  // visits: count, scan, fill, sort by (bucket, task)
+  // visits: count, scan, fill, sort by (bucket, hashed task index)
   const size_t nbuckets = ntiles * kLpBuckets * kNumClasses;
   unsigned int *d_count = nullptr, *d_start = nullptr;
   B200_CHECK(cudaMalloc((void **)&d_count, (nbuckets + 1) * sizeof(unsigned int)));
   B200_CHECK(cudaMalloc((void **)&d_start, (nbuckets + 1) * sizeof(unsigned int)));
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
   VisitGenArgs VA;
-  VA.ttasks = d_ttasks, VA.nttasks = (int)tt.size();
+  VA.ttasks = d_ttasks, VA.ctasks = cl.d_ctasks, VA.nttasks = (int)tt.size();
   VA.nx = L.npts_local[0], VA.ny = L.npts_local[1], VA.nz = L.npts_local[2];
   VA.Nx = L.npts_global[0], VA.Ny = L.npts_global[1], VA.Nz = L.npts_global[2];
   VA.ntx = ntx, VA.nty = nty, VA.ntz = ntz, VA.ntiles = (unsigned)ntiles;
@@ -332,8 +346,6 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
   visitgen_kernel<1><<<vg_blocks, 128, 0, s>>>(VA);
   B200_CHECK(cudaGetLastError());
   count_launch(4);
-  // Order every bucket by task: reproducible accumulation order, and neighbouring
-  // tiles walk the same tasks at about the same time (coefficients shared through L2).
   if (nvis > 1) {
     B200_CHECK(cudaMalloc((void **)&d_keys[1], nvis * sizeof(unsigned long long)));
     B200_CHECK(cudaMalloc((void **)&d_visits_alt, (nvis + 40) * sizeof(CVisit)));
@@ -362,7 +374,7 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
       if (e == f)
         continue;
       const int tx = (int)(b % ntx), ty = (int)((b / ntx) % nty), tz = (int)(b / ((size_t)ntx * nty));
-      const int cnt = (int)(e - f), nchunks = (cnt + kCtItemVisits - 1) / kCtItemVisits,
+      const int cnt = (int)(e - f), nchunks = (cnt + item_cap - 1) / item_cap,
                 per = (cnt + nchunks - 1) / nchunks;
       for (int c = 0; c < nchunks; c++) {
         CWork W;
@@ -453,26 +465,31 @@ template <bool COLLOCATE, int LPHI> struct CtSlot {
   static constexpr int PITCH = (LPHI + 2) / 2 * 2;  // doubles per table row (even: 16-byte rows)
   static constexpr int NCP = (ncoset(LPHI) + 1) / 2 * 2;
   static constexpr int HDR = 0;  // u32[16]: [0..1] plane ranges of the 8 warp blocks, [2] coefficient slot,
-                                 //          [3] lp, [4] active warp blocks, [5] the visit's sequence number
+                                 //          [3] lp, [4] active warp blocks, [5] the visit's sequence number,
+                                 //          [6] plane-mask table column of the visit (oz + bias)
   static constexpr int ROWS = 64;                   // x rows | y rows | z rows
-  static constexpr int CM = ROWS + 64 * PITCH * 8;  // u16 [2][16][16] plane masks
-  static constexpr int COEF = CM + 1024;            // collocate: C_xyz; integrate: partial results [8][NCP]
+  static constexpr int KT = ROWS + 64 * PITCH * 8;  // u8 [16][16]: K + 1 of the tile's columns (0: outside)
+  static constexpr int COEF = KT + 256;             // collocate: C_xyz; integrate: partial results [8][NCP]
   static constexpr int BYTES = COEF + (COLLOCATE ? NCP : 8 * NCP) * 8;
 };
+
+constexpr int kCtChunk = 16;   // visit records per staging chunk (one bulk copy)
+constexpr int kCtChunks = 4;   // staging ring depth
 
 template <bool COLLOCATE, int LPHI> struct CtConf {
   using Slot = CtSlot<COLLOCATE, LPHI>;
   // ring depth: as many slots as fit comfortably beside a second CTA (low classes)
-  static constexpr int NS = (Slot::BYTES <= 4096) ? 16 : ((Slot::BYTES <= 12288) ? 8 : 4);
-  static constexpr int BAR = 0;         // u64 full[NS], empty[NS]
-  static constexpr int ITEM = 16 * NS;  // int: the CTA's current work item
-  static constexpr int E2T = ITEM + 16; // double[64]: 2^(j/64)
-  static constexpr int ZM = E2T + 512;
-  static constexpr int SLOTS = ZM + kCtZmRows * kCtZmPitch * 4;
+  static constexpr int NS = (Slot::BYTES <= 3072) ? 32 : ((Slot::BYTES <= 6144) ? 16 : ((Slot::BYTES <= 12288) ? 8 : 4));
+  static constexpr int BAR = 0;                       // u64 full[NS], empty[NS], cfull[4], cempty[4]
+  static constexpr int ITEM = 16 * NS + 16 * kCtChunks;  // int: the CTA's current work item
+  static constexpr int E2T = ITEM + 16;               // double[64]: 2^(j/64)
+  static constexpr int ZM = E2T + 512;                // u16 [2][kCtZmRows][kCtZmPitch]: plane masks per z half
+  static constexpr int STAGE = ZM + 2 * kCtZmRows * kCtZmPitch * 2;  // CVisit [kCtChunks][kCtChunk]
+  static constexpr int SLOTS = STAGE + kCtChunks * kCtChunk * 64;
   static constexpr int BYTES = SLOTS + NS * Slot::BYTES;
 };
 
-extern __shared__ __align__(16) unsigned char ct_smem[];
+extern __shared__ __align__(128) unsigned char ct_smem[];
 
 // exp(-zl2 * d * d) for zl2 = zetp * log2(e): 2^y with y = n / 64 + f, |f| <= 1/128,
 // 2^(j/64) from a 64-entry table (shared memory) and a degree-5 polynomial for 2^f
@@ -563,7 +580,8 @@ struct CtWarp {
   int lane, warp;
   int xrow, yrow;  // table rows of my x and of my first y within the tile
   int zrow0;       // first z row of my warp block
-  int cm_off;      // byte offset of my first column's plane mask within the slot's mask array
+  int kt_off;      // my first column within the slot's K tile
+  const unsigned short *zm;  // plane-mask table of my z half
 };
 
 // ---- consumer: one visit, one warp (the visit is known to touch this warp block) ----
@@ -575,13 +593,16 @@ __device__ __forceinline__ void ct_consume(const unsigned char *__restrict__ slo
   constexpr int NC = ncoset(LP);
   const unsigned wr = reinterpret_cast<const unsigned char *>(slot + S::HDR)[c.warp];
   const int wlo = (int)(wr & 15u), whi = (int)(wr >> 4);
+  // sphere masks of my two columns: K + 1 from the staged tile of the sphere table, then the plane mask
+  const unsigned char *kt = slot + S::KT + c.kt_off;
+  const unsigned zcol = reinterpret_cast<const unsigned *>(slot + S::HDR)[6];
+  const unsigned mask0 = c.zm[(unsigned)kt[0] * kCtZmPitch + zcol];
+  const unsigned mask1 = c.zm[(unsigned)kt[4 * 16] * kCtZmPitch + zcol];
   const double *rows = reinterpret_cast<const double *>(slot + S::ROWS);
   double X[LP + 1], Y0[LP + 1], Y1[LP + 1];
   ct_load_row<LP>(rows + c.xrow * PITCH, X);
   ct_load_row<LP>(rows + c.yrow * PITCH, Y0);
   ct_load_row<LP>(rows + (c.yrow + 4) * PITCH, Y1);
-  const unsigned short *cm = reinterpret_cast<const unsigned short *>(slot + S::CM + c.cm_off);
-  const unsigned mask0 = cm[0], mask1 = cm[4 * 16];
   const double *tZ = rows + (32 + c.zrow0) * PITCH;
 
   if constexpr (COLLOCATE) {
@@ -669,15 +690,15 @@ __device__ __forceinline__ void ct_drain(const unsigned char *__restrict__ slot,
   }
 }
 
-// ---- producer: prepare one visit in its slot (one warp) --------------------
+// ---- producer: prepare one visit in its slot (one warp) from its staged record ----
 template <bool COLLOCATE, int LPHI>
 __device__ __forceinline__ void ct_produce(unsigned char *__restrict__ slot, const unsigned full_bar,
                                            const unsigned empty_bar, const CtLevelArgs &L, const CtArgs &A,
-                                           const unsigned *__restrict__ s_zm, const double *__restrict__ s_e2t,
-                                           const uint4 ra, const uint2 rb, const int lp, const unsigned seq,
-                                           const int lane) {
+                                           const double *__restrict__ s_e2t, const unsigned char *__restrict__ rec,
+                                           const int lp, const unsigned seq, const int lane) {
   using S = CtSlot<COLLOCATE, LPHI>;
   constexpr int PITCH = S::PITCH;
+  const uint4 ra = *reinterpret_cast<const uint4 *>(rec);
   const unsigned q = ra.x & 0xffffffu, act = ra.x >> 24;
   const int ox = (int)(signed char)(ra.z & 0xffu), oy = (int)(signed char)((ra.z >> 8) & 0xffu),
             oz = (int)(signed char)((ra.z >> 16) & 0xffu);
@@ -686,31 +707,21 @@ __device__ __forceinline__ void ct_produce(unsigned char *__restrict__ slot, con
     if (lane == 0)
       bulk_g2s(ct_smem_u32(slot + S::COEF), A.coef + cs, (unsigned)((ncoset(lp) + 1) / 2 * 16), full_bar);
   }
-  double roff_xy, roff_z, zl2;
-  {
-    const double2 *cp = reinterpret_cast<const double2 *>(L.ctasks + q);
-    const double2 a = __ldg(cp), b = __ldg(cp + 1);  // roff[3], zetp * log2(e)
-    roff_xy = (lane < 16) ? a.x : a.y, roff_z = b.x, zl2 = b.y;
-  }
-  // sphere extents of my 8 columns: row r = lane >> 1, columns 8 * (lane & 1) .. + 7
+  // sphere extents of my 8 columns (row r = lane >> 1, columns 8 * (lane & 1) .. + 7): issued
+  // first, needed last -- the table is small and mostly L1-resident
   const int r = lane >> 1, hf = lane & 1;
-  unsigned long long kbytes;
-  {
-    const unsigned char *kp = L.ktab + (ra.y + (unsigned)(r * kCtKPitch + 8 * hf));
-    const unsigned long long a = (unsigned long long)kp;
-    const uint2 *ap = reinterpret_cast<const uint2 *>(a & ~7ull);
-    const unsigned sh = (unsigned)(a & 7ull) * 8u;
-    const uint2 w0 = __ldg(ap), w1 = __ldg(ap + 1);
-    const unsigned long long lo = ((unsigned long long)w0.y << 32) | w0.x, hi = ((unsigned long long)w1.y << 32) | w1.x;
-    kbytes = (sh == 0u) ? lo : ((lo >> sh) | (hi << (64u - sh)));
-  }
+  const unsigned char *kp = L.ktab + (ra.y + (unsigned)(r * kCtKPitch + 8 * hf));
+  const unsigned long long ka = (unsigned long long)kp;
+  const uint2 *kap = reinterpret_cast<const uint2 *>(ka & ~7ull);
+  const uint2 kw0 = __ldg(kap), kw1 = __ldg(kap + 1);
   // 1-D tables: lanes 0-15 x, 16-31 y; then 32 z entries (two independent chains)
+  const double2 t0 = *reinterpret_cast<const double2 *>(rec + 32), t1 = *reinterpret_cast<const double2 *>(rec + 48);
   double *rows = reinterpret_cast<double *>(slot + S::ROWS);
   {
     const bool isy = lane >= 16;
-    const double d1 = (double)((lane & 15) - (isy ? oy : ox)) * (isy ? L.hy : L.hx) - roff_xy;
-    const double d2 = (double)(lane - oz) * L.hz - roff_z;
-    double e1 = ct_exp_neg(zl2, d1, s_e2t), e2 = ct_exp_neg(zl2, d2, s_e2t);
+    const double d1 = (double)((lane & 15) - (isy ? oy : ox)) * (isy ? L.hy : L.hx) - (isy ? t0.y : t0.x);
+    const double d2 = (double)(lane - oz) * L.hz - t1.x;
+    double e1 = ct_exp_neg(t1.y, d1, s_e2t), e2 = ct_exp_neg(t1.y, d2, s_e2t);
     double *row1 = rows + lane * PITCH, *row2 = rows + (32 + lane) * PITCH;
     row1[0] = e1, row2[0] = e2;
 #pragma unroll
@@ -720,27 +731,17 @@ __device__ __forceinline__ void ct_produce(unsigned char *__restrict__ slot, con
         row1[l] = e1, row2[l] = e2;
       }
   }
-  // plane masks of my columns, split into the two z halves of the tile
   {
-    unsigned m[8];
-    const unsigned *zrow = s_zm + (oz + kCtZmBias);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const unsigned k1 = (unsigned)(kbytes >> (8 * k)) & 0xffu;
-      m[k] = zrow[k1 * kCtZmPitch];
-    }
-    uint4 lo4, hi4;
-    lo4.x = __byte_perm(m[0], m[1], 0x5410), hi4.x = __byte_perm(m[0], m[1], 0x7632);
-    lo4.y = __byte_perm(m[2], m[3], 0x5410), hi4.y = __byte_perm(m[2], m[3], 0x7632);
-    lo4.z = __byte_perm(m[4], m[5], 0x5410), hi4.z = __byte_perm(m[4], m[5], 0x7632);
-    lo4.w = __byte_perm(m[6], m[7], 0x5410), hi4.w = __byte_perm(m[6], m[7], 0x7632);
-    uint4 *cm = reinterpret_cast<uint4 *>(slot + S::CM);
-    cm[r * 2 + hf] = lo4;       // [0][r][8 hf ..]
-    cm[32 + r * 2 + hf] = hi4;  // [1][r][8 hf ..]
+    const unsigned sh = (unsigned)(ka & 7ull) * 8u;
+    const unsigned long long lo = ((unsigned long long)kw0.y << 32) | kw0.x, hi = ((unsigned long long)kw1.y << 32) | kw1.x;
+    const unsigned long long kbytes = (sh == 0u) ? lo : ((lo >> sh) | (hi << (64u - sh)));
+    *reinterpret_cast<unsigned long long *>(slot + S::KT + r * 16 + 8 * hf) = kbytes;
   }
   if (lane == 0) {
     unsigned *hdr = reinterpret_cast<unsigned *>(slot + S::HDR);
+    const uint2 rb = *reinterpret_cast<const uint2 *>(rec + 16);
     hdr[0] = rb.x, hdr[1] = rb.y;
+    hdr[6] = (unsigned)(oz + kCtZmBias);
     if constexpr (!COLLOCATE)
       hdr[2] = cs, hdr[3] = (unsigned)lp, hdr[4] = act;
   }
@@ -766,8 +767,9 @@ __device__ __forceinline__ void ct_produce(unsigned char *__restrict__ slot, con
 template <bool COLLOCATE, int LPHI> struct CtRing {
   using Conf = CtConf<COLLOCATE, LPHI>;
   using S = CtSlot<COLLOCATE, LPHI>;
-  unsigned bar0;   // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (NS + s)
+  unsigned bar0;   // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (NS + s), then cfull[4], cempty[4]
   unsigned gbase;  // visits this CTA has been through before the current item (slot = g % NS, use = g / NS)
+  unsigned cbase;  // staging chunks ... (buffer = k % kCtChunks, use = k / kCtChunks)
   int vbeg, vend;  // the item's visits (absolute indices into the level's visit array)
   int e0, e1;      // ends of the class's first and second lp within the item
   __device__ __forceinline__ unsigned char *slot(const unsigned s) const {
@@ -775,6 +777,10 @@ template <bool COLLOCATE, int LPHI> struct CtRing {
   }
   __device__ __forceinline__ unsigned full(const unsigned s) const { return bar0 + 8u * s; }
   __device__ __forceinline__ unsigned empty(const unsigned s) const { return bar0 + 8u * (Conf::NS + s); }
+  __device__ __forceinline__ unsigned cfull(const unsigned b) const { return bar0 + 8u * (2 * Conf::NS + b); }
+  __device__ __forceinline__ unsigned cempty(const unsigned b) const {
+    return bar0 + 8u * (2 * Conf::NS + kCtChunks + b);
+  }
 };
 
 // All visits [lo, hi) of ONE lp of the item, as seen by one consumer warp: it peeks at
@@ -801,7 +807,7 @@ __device__ __forceinline__ void ct_consumer_run(const CtRing<COLLOCATE, LPHI> &R
       {
         const volatile unsigned *seq = reinterpret_cast<const volatile unsigned *>(R.slot(s) + CtSlot<COLLOCATE, LPHI>::HDR + 20);
         while (*seq != g + 1u)
-          __nanosleep(32);
+          __nanosleep(20);
       }
       mbar_wait(R.full(s), use & 1u);
       ct_consume<COLLOCATE, LP, LPHI>(R.slot(s), c, acc0, acc1);
@@ -812,36 +818,56 @@ __device__ __forceinline__ void ct_consumer_run(const CtRing<COLLOCATE, LPHI> &R
   }
 }
 
-// The producer warps of a CTA take the item's visits round-robin.
+// The producer warps of a CTA: the item's visit records are streamed into a staging ring
+// in chunks of kCtChunk (one bulk-async copy each, issued two chunks ahead by the first
+// producer warp); inside a chunk the four warps take the visits round-robin.
 template <bool COLLOCATE, int LPLO, int LPHI>
 __device__ __forceinline__ void ct_producer_run(const CtRing<COLLOCATE, LPHI> &R, const CtLevelArgs &L,
-                                                const CtArgs &A, const unsigned *__restrict__ s_zm,
-                                                const double *__restrict__ s_e2t, const int pw, const int lane) {
-  constexpr int NS = CtConf<COLLOCATE, LPHI>::NS;
+                                                const CtArgs &A, const double *__restrict__ s_e2t, const int pw,
+                                                const int lane) {
+  using Conf = CtConf<COLLOCATE, LPHI>;
+  constexpr int NS = Conf::NS;
   const int nvis = R.vend - R.vbeg;
-  for (int ord = pw; ord < nvis; ord += kCtProducers) {
-    const int v = R.vbeg + ord;
-    const uint4 ra = __ldg(&L.visits[v].a);
-    const uint2 rb = __ldg(reinterpret_cast<const uint2 *>(&L.visits[v].b));
-    {  // warm the caches for my next visit: its record, its task and its sphere-table rows
-      const CVisit *nv = &L.visits[v + kCtProducers];
-      const unsigned nq = __ldg(&nv->a.x) & 0xffffffu, nk = __ldg(&nv->a.y);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(L.ctasks + nq));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(L.ktab + (nk + (unsigned)((lane >> 1) * kCtKPitch))));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(nv + kCtProducers));
-    }
-    const unsigned g = R.gbase + (unsigned)ord;
-    const unsigned s = g % NS, use = g / NS;
-    unsigned char *slot = R.slot(s);
-    mbar_wait(R.empty(s), (use & 1u) ^ 1u);
-    if constexpr (!COLLOCATE) {
-      if (ord >= NS) {  // the slot's previous visit belongs to this item: fold its results
-        ct_drain<LPHI>(slot, A.coef, lane);
-        __syncwarp();
+  const int nch = (nvis + kCtChunk - 1) / kCtChunk;
+  auto request = [&](const int c) {  // loader thread only
+    const unsigned k = R.cbase + (unsigned)c, b = k % kCtChunks, cu = k / kCtChunks;
+    mbar_wait(R.cempty(b), (cu & 1u) ^ 1u);
+    const unsigned bytes = (unsigned)min(kCtChunk, nvis - c * kCtChunk) * 64u;
+    mbar_arrive_expect_tx(R.cfull(b), bytes);
+    bulk_g2s(ct_smem_u32(ct_smem + Conf::STAGE + b * (kCtChunk * 64)), L.visits + (R.vbeg + c * kCtChunk), bytes,
+             R.cfull(b));
+  };
+  const bool loader = (pw == 0 && lane == 0);
+  if (loader) {
+    request(0);
+    if (nch > 1)
+      request(1);
+  }
+  for (int c = 0; c < nch; c++) {
+    if (loader && c + 2 < nch)
+      request(c + 2);
+    const unsigned k = R.cbase + (unsigned)c, b = k % kCtChunks, cu = k / kCtChunks;
+    mbar_wait(R.cfull(b), cu & 1u);
+    const unsigned char *stage = ct_smem + Conf::STAGE + b * (kCtChunk * 64);
+    const int clen = min(kCtChunk, nvis - c * kCtChunk);
+    for (int j = pw; j < clen; j += kCtProducers) {
+      const int ord = c * kCtChunk + j, v = R.vbeg + ord;
+      const unsigned g = R.gbase + (unsigned)ord;
+      const unsigned s = g % NS, use = g / NS;
+      unsigned char *slot = R.slot(s);
+      mbar_wait(R.empty(s), (use & 1u) ^ 1u);
+      if constexpr (!COLLOCATE) {
+        if (ord >= NS) {  // the slot's previous visit belongs to this item: fold its results
+          ct_drain<LPHI>(slot, A.coef, lane);
+          __syncwarp();
+        }
       }
+      const int lp = LPLO + (v >= R.e0 ? 1 : 0) + (v >= R.e1 ? 1 : 0);
+      ct_produce<COLLOCATE, LPHI>(slot, R.full(s), R.empty(s), L, A, s_e2t, stage + j * 64, lp, g + 1u, lane);
     }
-    const int lp = LPLO + (v >= R.e0 ? 1 : 0) + (v >= R.e1 ? 1 : 0);
-    ct_produce<COLLOCATE, LPHI>(slot, R.full(s), R.empty(s), L, A, s_zm, s_e2t, ra, rb, lp, g + 1u, lane);
+    __syncwarp();
+    if (lane == 0)
+      mbar_arrive(R.cempty(b));
   }
   if constexpr (!COLLOCATE) {
     // fold the results of the item's last visits (nobody recycles their slots within the item)
@@ -855,12 +881,12 @@ __device__ __forceinline__ void ct_producer_run(const CtRing<COLLOCATE, LPHI> &R
   }
 }
 
-// Register budgets of the two roles (setmaxnreg; 2 CTAs of 12 warps per SM:
-// (8 * RC + 4 * RP) * 32 <= 32768).
+// Register budgets of the two roles (setmaxnreg moves registers inside the CTA's own
+// allocation: 8 RC + 4 RP <= 12 LAUNCH).
 template <int LPHI> struct CtRegs {
   static constexpr int CTAS = (LPHI <= 2) ? 2 : 1;
   static constexpr int LAUNCH = (LPHI <= 2) ? 80 : 168;
-  static constexpr int CONSUMER = (LPHI <= 2) ? 96 : 216;  // (the pool is the CTA's own: 8 RC + 4 RP <= 12 LAUNCH)
+  static constexpr int CONSUMER = (LPHI <= 2) ? 96 : 216;
   static constexpr int PRODUCER = (LPHI <= 2) ? 48 : 72;
 };
 
@@ -869,14 +895,17 @@ __global__ void __launch_bounds__(kCtThreads, CtRegs<LPHI>::CTAS) ctile_kernel(c
   using Conf = CtConf<COLLOCATE, LPHI>;
   constexpr int NS = Conf::NS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned *s_zm = reinterpret_cast<unsigned *>(ct_smem + Conf::ZM);
+  unsigned short *s_zm = reinterpret_cast<unsigned short *>(ct_smem + Conf::ZM);
   double *s_e2t = reinterpret_cast<double *>(ct_smem + Conf::E2T);
   int *s_item = reinterpret_cast<int *>(ct_smem + Conf::ITEM);
   CtRing<COLLOCATE, LPHI> R;
   R.bar0 = ct_smem_u32(ct_smem + Conf::BAR);
-  R.gbase = 0u;
-  for (int q = tid; q < kCtZmRows * kCtZmPitch; q += kCtThreads)
-    s_zm[q] = A.zmask[q];
+  R.gbase = 0u, R.cbase = 0u;
+  for (int q = tid; q < kCtZmRows * kCtZmPitch; q += kCtThreads) {  // split the plane masks per z half
+    const unsigned m = A.zmask[q];
+    s_zm[q] = (unsigned short)(m & 0xffffu);
+    s_zm[kCtZmRows * kCtZmPitch + q] = (unsigned short)(m >> 16);
+  }
   if (tid < 64)
     s_e2t[tid] = exp2((double)tid * (1.0 / 64.0));
   if (tid < NS)
@@ -885,6 +914,10 @@ __global__ void __launch_bounds__(kCtThreads, CtRegs<LPHI>::CTAS) ctile_kernel(c
     for (int s = 0; s < NS; s++) {
       mbar_init(R.full(s), 1);
       mbar_init(R.empty(s), kCtConsumers);
+    }
+    for (int b = 0; b < kCtChunks; b++) {
+      mbar_init(R.cfull(b), 1);
+      mbar_init(R.cempty(b), kCtProducers);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -908,8 +941,9 @@ __global__ void __launch_bounds__(kCtThreads, CtRegs<LPHI>::CTAS) ctile_kernel(c
       R.vbeg = W1.x, R.vend = W1.w;
       R.e0 = (LPLO + 1 <= LPHI) ? W1.y : W1.w;
       R.e1 = (LPLO + 2 <= LPHI) ? W1.z : W1.w;
-      ct_producer_run<COLLOCATE, LPLO, LPHI>(R, L, A, s_zm, s_e2t, pw, lane);
+      ct_producer_run<COLLOCATE, LPLO, LPHI>(R, L, A, s_e2t, pw, lane);
       R.gbase += (unsigned)(R.vend - R.vbeg);
+      R.cbase += (unsigned)((R.vend - R.vbeg + kCtChunk - 1) / kCtChunk);
     }
     return;
   }
@@ -923,7 +957,8 @@ __global__ void __launch_bounds__(kCtThreads, CtRegs<LPHI>::CTAS) ctile_kernel(c
   c.xrow = 8 * bx + li;
   c.yrow = 16 + 8 * by + lj;
   c.zrow0 = 16 * bz;
-  c.cm_off = ((bz * 16 + 8 * by + lj) * 16 + 8 * bx + li) * 2;
+  c.kt_off = (8 * by + lj) * 16 + 8 * bx + li;
+  c.zm = s_zm + bz * (kCtZmRows * kCtZmPitch);
 
   for (;;) {
     __syncthreads();

@@ -714,8 +714,12 @@ static void build_task_list(
   for (int l = 0; l < nlevels; l++) {
     LevelInfo &li = tl.linfo[l];
     std::vector<int> generic_ids;
-    if (tl.path == 0)
-      build_ctile_level(li.ctile, l, tl.levels[l], tl.h_tasks, li.first, li.last, generic_ids, s);
+    if (tl.path == 0) {
+      // work items of at most item_cap visits: about a dozen items per resident CTA (a task makes
+      // about 8 visits), capped so that a tile's accumulators are not flushed too often
+      const int item_cap = (int)std::min<double>(kCtItemVisits, std::max(256.0, 8.5 * ntasks / (148.0 * 2 * 12)));
+      build_ctile_level(li.ctile, l, tl.levels[l], tl.h_tasks, li.first, li.last, generic_ids, item_cap, s);
+    }
     else
       build_tiled_level(li.tiled, tl.levels[l], tl.h_tasks, tl.d_tasks.p, li.first, li.last, generic_ids, s);
     li.n_generic = (int)generic_ids.size();
