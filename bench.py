@@ -179,9 +179,9 @@ def reference_gpu_timing(wl, steps, warmup, forces, virial=False, device=0):
     times, tc, ti = [], [], []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        tl.collocate(100, pab, grids)
+        tl.collocate(FUNC, pab, grids)
         t1 = time.perf_counter()
-        tl.integrate(False, pab if forces else None, grids, hab, f, v)
+        tl.integrate(TAU, pab if forces else None, grids, hab, f, v)
         t2 = time.perf_counter()
         if i >= warmup:
             times.append(t2 - t0), tc.append(t1 - t0), ti.append(t2 - t1)
@@ -217,11 +217,13 @@ def run_reference_gpu(args):
 
 
 METRIC = "grid collocate+integrate model FP64 GFLOP/s per SCF step (s/SCF-step = ms_per_step/1000)"
+FUNC, TAU = 100, False  # GRID_FUNC_AB, no tau; --tau switches to GRID_FUNC_DADB (200) + compute_tau
 
 
 def bench_config(wl, args, extra=None):
     cfg = {"workload": f"{args.workload} GPW {wl.meta['basis']} cutoff 280 Ry rel_cutoff 30 Ry 4 levels "
-                       f"{wl.meta['npts']}; step = collocate(GRID_FUNC_AB) + integrate"
+                       f"{wl.meta['npts']}; step = collocate({'GRID_FUNC_DADB' if getattr(args, 'tau', False) else 'GRID_FUNC_AB'}) + "
+                       f"integrate{'(compute_tau)' if getattr(args, 'tau', False) else ''}"
                        + ("+forces" if args.forces else "") + ("+virial" if getattr(args, "virial", False) else ""),
            "ntasks": wl.ntasks, "nblocks": wl.nblocks, "natoms": wl.natoms,
            "l2": "per-step working set (task records + P/H blocks + grids > 0.5 GB) exceeds the 126 MB L2",
@@ -261,8 +263,8 @@ def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0, virial=False)
         times = []
         for i in range(nwarm + nsteps):
             t0 = time.perf_counter()
-            tl.collocate(100, pab, grids)
-            tl.integrate(False, pab if forces else None, grids, hab, f, v)
+            tl.collocate(FUNC, pab, grids)
+            tl.integrate(TAU, pab if forces else None, grids, hab, f, v)
             dt = time.perf_counter() - t0
             if i >= nwarm:
                 times.append(dt)
@@ -334,9 +336,14 @@ def main():
                     help="TZV2P-GTH as shipped in benchmarks/QS/H2O-N.inp; DZVP-MOLOPT-SR-GTH is BASELINE config 2's")
     ap.add_argument("--forces", action="store_true", help="integrate with forces (BASELINE config 3)")
     ap.add_argument("--virial", action="store_true", help="... and the virial (implies --forces)")
+    ap.add_argument("--tau", action="store_true",
+                    help="meta-GGA step (BASELINE config 4): collocate GRID_FUNC_DADB, integrate with compute_tau")
     ap.add_argument("--cpu-budget", type=float, default=600.0,
                     help="seconds the CPU reference may take over all its steps before its task list is thinned "
                          "(the default covers the full H2O-256 / H2O-1024 lists: same config as the GPU arm)")
+    ap.add_argument("--no-verify", action="store_true",
+                    help="N > 1: skip the (untimed) comparison of the N-rank grids and H blocks with a "
+                         "1-GPU run of the full task list")
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the reference-CUDA-backend leg of the N=1 line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -349,6 +356,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     args.forces = args.forces or args.virial
+    global FUNC, TAU
+    FUNC, TAU = (200, True) if args.tau else (100, False)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -404,7 +413,13 @@ def main():
         hab_exchange = rsgrid.HabExchange(wl_full, slab_levels, rank, world) if args.slab_compact else None
     else:
         wl = split_blocks(wl_full, world, rank)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    t_create = time.perf_counter()
     tl = wl.create(lib)
+    torch.cuda.synchronize()
+    create_ms = (time.perf_counter() - t_create) * 1e3
+    table_bytes = free0 - torch.cuda.mem_get_info()[0]  # device memory the task list holds
     st = lib.stats(tl)
     flops_local = st["flops_collocate"] + st["flops_integrate"]
     flops_t = torch.tensor([flops_local, st["flops_collocate"], st["flops_integrate"], st["npts_model"]],
@@ -438,9 +453,9 @@ def main():
             rsgrid.halo_fill(t, sl, rank, world, dist)  # potential: owners -> halos
 
     def step_resident():
-        tl.collocate(100, pab, grids)
+        tl.collocate(FUNC, pab, grids)
         exchange(grids)
-        tl.integrate(False, pab if args.forces else None, grids, hab, forces, virial)
+        tl.integrate(TAU, pab if args.forces else None, grids, hab, forces, virial)
         if slab_levels is not None:  # a block's tasks may live on several slabs
             if hab_exchange is not None:
                 hab_exchange.reduce(hab.device[: wl.pab_len], dist)
@@ -518,17 +533,17 @@ def main():
         if world == 1:
             # host buffers through the public API: the library pipelines the P/H block
             # copies against its coefficient kernels and copies the grids per level
-            tl.collocate(100, pab_e, grids_e)  # H2D pab, kernels, D2H grids
-            tl.integrate(False, pab_e if args.forces else None, grids_e, hab_e, forces, virial)  # H2D grids, D2H hab
+            tl.collocate(FUNC, pab_e, grids_e)  # H2D pab, kernels, D2H grids
+            tl.integrate(TAU, pab_e if args.forces else None, grids_e, hab_e, forces, virial)  # H2D grids, D2H hab
             return
         # N > 1: the grids stay on the device between collocate, the exchange and
         # integrate (device_buffer authoritative); this rank's P blocks come from
         # pinned host memory and its H blocks go back to it every step
         lib.set_device_resident(True)
         pab.device.copy_(pin_pab, non_blocking=True)
-        tl.collocate(100, pab, grids)
+        tl.collocate(FUNC, pab, grids)
         exchange(grids)
-        tl.integrate(False, pab if args.forces else None, grids, hab, forces, virial)
+        tl.integrate(TAU, pab if args.forces else None, grids, hab, forces, virial)
         if slab_levels is not None:
             if hab_exchange is not None:
                 hab_exchange.reduce(hab.device[: wl.pab_len], dist)
@@ -555,6 +570,62 @@ def main():
     else:  # per rank: its P blocks in, its H blocks out (the grids never leave the device)
         h2d = 8 * wl.pab_len
         d2h = 8 * wl.pab_len
+
+    # ---- N > 1: the distributed result against a single-GPU run of the full list (untimed) ----
+    parity = None
+    if world > 1 and not args.no_verify:
+        from cp2k_b200.workload import block_index_map
+
+        lib.set_device_resident(True)
+        pab_full = wl_full.random_pab(7)
+        idx = block_index_map(wl) if "parent_block_ids" in wl.meta else None
+        pab.device[: wl.pab_len].copy_(torch.from_numpy(pab_full.host[idx] if idx is not None else pab_full.host))
+        tl.collocate(FUNC, pab, grids)
+        exchange(grids)
+        tl.integrate(TAU, None, grids, hab, None, None)
+        own_hab, own_ref_slice = hab.device[: wl.pab_len], idx
+        if slab_levels is not None:
+            if hab_exchange is not None:
+                own_hab = hab_exchange.reduce(hab.device[: wl.pab_len], dist)
+                own_ref_slice = slice(hab_exchange.owned_start, hab_exchange.owned_start + hab_exchange.owned_len)
+            else:
+                dist.all_reduce(hab.device)
+        torch.cuda.synchronize()
+        # the reference: this rank alone on the whole task list
+        tl1 = wl_full.create(lib)
+        pab1 = OffloadBuffer.with_device(wl_full.pab_len)
+        pab1.device.copy_(torch.from_numpy(pab_full.host))
+        grids1 = [OffloadBuffer.with_device(l.npts_local_total) for l in wl_full.layouts]
+        hab1 = OffloadBuffer.with_device(wl_full.pab_len)
+        tl1.collocate(FUNC, pab1, grids1)
+        tl1.integrate(TAU, None, grids1, hab1, None, None)
+        torch.cuda.synchronize()
+
+        def rel(a, b):
+            if a.numel() == 0:
+                return 0.0
+            return float(((a - b).abs() / b.abs().clamp(min=1.0)).max().item())
+
+        gerr = 0.0
+        for l, (lay, g, g1) in enumerate(zip(wl.layouts, grids, grids1)):
+            n, ng = lay.npts_local, wl_full.layouts[l].npts_global
+            mine = g.device[: int(n[0]) * int(n[1]) * int(n[2])].view(int(n[2]), int(n[1]), int(n[0]))
+            ref = g1.device.view(int(ng[2]), int(ng[1]), int(ng[0]))
+            if slab_levels is not None and slab_levels[l].distributed:
+                planes = torch.from_numpy(np.asarray(slab_levels[l].local_planes(rank))).to("cuda")
+                ref = ref[planes]  # after the halo fill every local plane equals the global one
+            gerr = max(gerr, rel(mine, ref))
+        ref_h = hab1.device if own_ref_slice is None else hab1.device[
+            torch.from_numpy(own_ref_slice).to("cuda") if isinstance(own_ref_slice, np.ndarray) else own_ref_slice]
+        herr = rel(own_hab, ref_h)
+        errs = torch.tensor([gerr, herr], dtype=torch.float64, device="cuda")
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        parity = {"vs": "1-GPU run of the full task list on every rank, |d|/max(1,|ref|)",
+                  "grid_max_rel": float(errs[0]), "hab_max_rel": float(errs[1]), "tol": 1e-10}
+        tl1.free()
+        del grids1, hab1, pab1
+        torch.cuda.empty_cache()
+        assert parity["grid_max_rel"] < 1e-10 and parity["hab_max_rel"] < 1e-10, f"multi-GPU parity failed: {parity}"
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -594,6 +665,9 @@ def main():
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu,
+            "multi_gpu_parity": parity,
+            "create_task_list": {"ms": create_ms, "device_bytes": int(table_bytes),
+                                 "in_steps": create_ms / ms_per_step},
         }
         print(json.dumps(line))
     if tl is not None:

@@ -256,7 +256,9 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
       X.nb[d] = -T.lb_cube[d];
       max_nb = std::max(max_nb, X.nb[d]);
     }
-    X.n = n, X.lp0 = T.la_max + T.lb_max, X.task = it, X.epack = 0u;
+    X.n = n, X.lp0 = T.la_max + T.lb_max, X.task = it;
+    X.zl2 = T.zetp * 1.4426950408889634074;
+    X.pad[0] = X.pad[1] = X.pad[2] = 0;
     tt.push_back(X);
     max_n = std::max(max_n, n);
     max_lp0 = std::max(max_lp0, X.lp0);
@@ -276,7 +278,7 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
     cl.class_tt_first[lp_class(tt[q].lp0) + 1]++;
     for (int d = 0; d < 3; d++)
       ct[q].roff[d] = tt[q].roff[d];
-    ct[q].zl2 = tasks[tt[q].task].zetp * 1.4426950408889634074;
+    ct[q].zl2 = tt[q].zl2;
   }
   for (int c = 0; c < kNumClasses; c++)
     cl.class_tt_first[c + 1] += cl.class_tt_first[c];
@@ -491,28 +493,6 @@ template <bool COLLOCATE, int LPHI> struct CtConf {
 
 extern __shared__ __align__(128) unsigned char ct_smem[];
 
-// exp(-zl2 * d * d) for zl2 = zetp * log2(e): 2^y with y = n / 64 + f, |f| <= 1/128,
-// 2^(j/64) from a 64-entry table (shared memory) and a degree-5 polynomial for 2^f
-// (truncation error 4e-17); relative error ~ 2 ulp plus |y| * 1.1e-16 from forming y.
-// The binary exponent is clamped so that arguments far outside a task's cube (never
-// used by anyone) still give finite numbers.
-__device__ __forceinline__ double ct_exp_neg(const double zl2, const double d, const double *__restrict__ e2t) {
-  const double y = -zl2 * (d * d);
-  const double magic = 105553116266496.0;  // 1.5 * 2^46: one ulp is 1/64
-  const double t = y + magic;
-  const int n = __double2loint(t);
-  const double f = y - (t - magic);
-  double p = 1.3333558146428443e-03;           // ln2^5 / 120
-  p = fma(p, f, 9.6181291076284772e-03);       // ln2^4 / 24
-  p = fma(p, f, 5.5504108664821580e-02);       // ln2^3 / 6
-  p = fma(p, f, 2.4022650695910071e-01);       // ln2^2 / 2
-  p = fma(p, f, 6.9314718055994531e-01);       // ln2
-  p = fma(p, f, 1.0);
-  const double r = e2t[n & 63] * p;
-  const int k = max(n >> 6, -1000);
-  return __hiloint2double(__double2hiint(r) + (k << 20), __double2loint(r));
-}
-
 // Loads LP+1 doubles of a 16-byte aligned table row.
 template <int LP> __device__ __forceinline__ void ct_load_row(const double *__restrict__ row, double (&z)[LP + 1]) {
 #pragma unroll
@@ -721,7 +701,7 @@ __device__ __forceinline__ void ct_produce(unsigned char *__restrict__ slot, con
     const bool isy = lane >= 16;
     const double d1 = (double)((lane & 15) - (isy ? oy : ox)) * (isy ? L.hy : L.hx) - (isy ? t0.y : t0.x);
     const double d2 = (double)(lane - oz) * L.hz - t1.x;
-    double e1 = ct_exp_neg(t1.y, d1, s_e2t), e2 = ct_exp_neg(t1.y, d2, s_e2t);
+    double e1 = exp_neg_tab(t1.y, d1, s_e2t), e2 = exp_neg_tab(t1.y, d2, s_e2t);
     double *row1 = rows + lane * PITCH, *row2 = rows + (32 + lane) * PITCH;
     row1[0] = e1, row2[0] = e2;
 #pragma unroll

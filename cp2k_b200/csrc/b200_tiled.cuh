@@ -80,21 +80,45 @@ __host__ __device__ inline int lp_class(const int lp0) { return lp0 <= 2 ? 0 : (
 constexpr int kClassLo[kNumClasses] = {0, 3, 5};
 constexpr int kClassHi[kNumClasses] = {2, 4, 6};
 
-struct TTask {            // static per-task data of the tiled path
+struct alignas(16) TTask {  // static per-task data of the tiled path (80 bytes)
   double roff[3];
+  double zl2;             // zetp * log2(e): exp(-zetp d^2) = 2^(-zl2 d^2)
   int cc[3];              // cubecenter - shift_local (not wrapped)
   int nb[3];              // -lb_cube per axis
   int n;                  // discretised radius index
   int lp0;                // la_max + lb_max
   int task;               // index into the TaskDev array
-  unsigned epack;         // exp-table locator: (first double of the task's block / 4) << 5 | nbq
+  int pad[3];
 };
+
+// exp(-zl2 * d * d) for zl2 = zetp * log2(e): 2^y with y = n / 64 + f, |f| <= 1/128,
+// 2^(j/64) from a 64-entry table (shared memory) and a degree-5 polynomial for 2^f
+// (truncation error 4e-17); relative error ~ 2 ulp plus |y| * 1.1e-16 from forming y.
+// The binary exponent is clamped so that arguments far outside a task's cube (never
+// used by anyone) still give finite numbers.  17 instructions: the kernels compute their
+// 1-D Gaussian tables with it instead of reading per-task tables from HBM.
+__device__ __forceinline__ double exp_neg_tab(const double zl2, const double d, const double *__restrict__ e2t) {
+  const double y = -zl2 * (d * d);
+  const double magic = 105553116266496.0;  // 1.5 * 2^46: one ulp is 1/64
+  const double t = y + magic;
+  const int n = __double2loint(t);
+  const double f = y - (t - magic);
+  double p = 1.3333558146428443e-03;           // ln2^5 / 120
+  p = fma(p, f, 9.6181291076284772e-03);       // ln2^4 / 24
+  p = fma(p, f, 5.5504108664821580e-02);       // ln2^3 / 6
+  p = fma(p, f, 2.4022650695910071e-01);       // ln2^2 / 2
+  p = fma(p, f, 6.9314718055994531e-01);       // ln2
+  p = fma(p, f, 1.0);
+  const double r = e2t[n & 63] * p;
+  const int k = max(n >> 6, -1000);
+  return __hiloint2double(__double2hiint(r) + (k << 20), __double2loint(r));
+}
 
 struct alignas(16) TPair {  // 16 bytes, read as one uint4 (warp-uniform)
   unsigned q;             // ttask index
   unsigned kbase;         // sphere-table index of block column (0,0)
   unsigned opk;           // bytes 0, 1, 3: cube centre (x, y, z) relative to the block origin (signed); byte 2: wlo | whi << 4
-  unsigned epack;         // the task's exp-table locator (TTask::epack)
+  unsigned spare;
 };
 
 struct alignas(16) TWork {  // 32 bytes
@@ -121,7 +145,6 @@ struct TiledLevel {
   int ntasks_tiled = 0;
   int max_lp0 = 0;
   int max_n = 0;
-  int P = 0;              // exp-table pitch per axis: entries g = -P/2+1 .. P/2
   TTask *d_ttasks = nullptr;
   TPair *d_pairs = nullptr;
   TWork *d_work = nullptr;
@@ -129,10 +152,9 @@ struct TiledLevel {
   KTabHeader *d_khead = nullptr;
   unsigned char *d_ktab = nullptr;   // K+1 per (n, dj, di), 0 outside the sphere
   unsigned short *d_zmask = nullptr; // [kZmRows][kZmPitch]
-  double *d_etab = nullptr;          // [ttask][3][P]
   void release() {
     cudaFree(d_ttasks), cudaFree(d_pairs), cudaFree(d_work), cudaFree(d_khead), cudaFree(d_ktab);
-    cudaFree(d_etab), cudaFree(d_zmask);
+    cudaFree(d_zmask);
     cudaFree(d_counters);
     d_counters = nullptr;
     for (auto &p : d_class_task_ids) {
@@ -140,7 +162,7 @@ struct TiledLevel {
       p = nullptr;
     }
     d_ttasks = nullptr, d_pairs = nullptr, d_work = nullptr, d_khead = nullptr, d_ktab = nullptr;
-    d_etab = nullptr, d_zmask = nullptr;
+    d_zmask = nullptr;
     npairs = 0, nwork = 0, ntasks_tiled = 0;
   }
 };
@@ -305,7 +327,7 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
                 P.kbase = (unsigned)(H.offset + (X.nb[1] + kKPad - oy) * kKPitch + (X.nb[0] + kKPad - ox));
                 P.opk = ((unsigned)ox & 0xffu) | (((unsigned)oy & 0xffu) << 8) | (((unsigned)oz & 0xffu) << 24) |
                         ((unsigned)wlo << 16) | ((unsigned)whi << 20);
-                P.epack = X.epack;
+                P.spare = 0u;
                 A.pairs[pos] = P;
                 A.keys[pos] = ((unsigned long long)bucket << A.qbits) | (unsigned long long)q;
               }
@@ -315,43 +337,6 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
       }
     }
   }
-}
-
-// exp tables.  A task's block starts at double 4 * (epack >> 5) and holds, with
-// nbq = the task's largest cube half-width (epack & 31):
-//   [roff_x, roff_y, roff_z, 0]
-//   x row: exp(-zetp (g*h - roff)^2) for g = -nbq-7  .. nbq+8    (2 nbq + 16 entries)
-//   y row: likewise                                               (2 nbq + 16 entries)
-//   z row:                           for g = -nbq-15 .. nbq+16   (2 nbq + 32 entries)
-// with zeros outside the cube [-nb, nb+1].  The rows cover every offset a block that
-// overlaps the cube can ask for (block extents 8, 8, 16), so the kernels index them
-// without clamping.  Blocks are sized per task (not per level).
-__host__ __device__ inline int etab_doubles(const int nbq) { return (6 * nbq + 68 + 3) / 4 * 4; }
-__global__ void etab_kernel(const TTask *ttasks, const TaskDev *tasks, const int nttasks, const int Pmax,
-                            const double hx, const double hy, const double hz, double *etab) {
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)nttasks * Pmax)
-    return;
-  const int e = (int)(idx % Pmax), q = (int)(idx / Pmax);
-  const TTask &X = ttasks[q];
-  const int nbq = (int)(X.epack & 31u), rx = 2 * nbq + 16;
-  if (e >= etab_doubles(nbq))
-    return;
-  double v = 0.0;
-  if (e < 4) {
-    if (e < 3)
-      v = X.roff[e];
-  } else if (e < 4 + 2 * rx + (2 * nbq + 32)) {
-    const int r = e - 4;
-    const int d = (r < rx) ? 0 : ((r < 2 * rx) ? 1 : 2);
-    const int g = r - d * rx - nbq - ((d == 2) ? 15 : 7);
-    if (g >= -X.nb[d] && g <= X.nb[d] + 1) {
-      const double h = (d == 0) ? hx : ((d == 1) ? hy : hz);
-      const double x = g * h - X.roff[d];
-      v = exp(-tasks[X.task].zetp * x * x);
-    }
-  }
-  etab[(size_t)4 * (X.epack >> 5) + e] = v;
 }
 
 // ---------------------------------------------------------------------------
@@ -393,6 +378,8 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
       max_nb = std::max(max_nb, X.nb[d]);
     }
     X.n = n, X.lp0 = T.la_max + T.lb_max, X.task = it;
+    X.zl2 = T.zetp * 1.4426950408889634074;
+    X.pad[0] = X.pad[1] = X.pad[2] = 0;
     tt.push_back(X);
     max_n = std::max(max_n, n);
     max_lp0 = std::max(max_lp0, X.lp0);
@@ -424,16 +411,6 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
     B200_ASSERT(heads[X.n].offset >= 0 && X.nb[0] == heads[X.n].nbx && X.nb[1] == heads[X.n].nby &&
                     X.nb[2] == heads[X.n].nbz,
                 "cube bounds disagree with the sphere table");
-  // exp-table locators (after the class sort: q is final)
-  size_t etab_len = 0;
-  for (TTask &X : tt) {
-    const int nbq = std::max(X.nb[0], std::max(X.nb[1], X.nb[2]));
-    B200_ASSERT(nbq < 32 && etab_len / 4 < ((size_t)1 << 27), "exp table too large for its 27-bit locator");
-    X.epack = (unsigned)((etab_len / 4) << 5) | (unsigned)nbq;
-    etab_len += (size_t)etab_doubles(nbq);
-  }
-  tl.P = etab_doubles(max_nb);
-
   auto up = [&](auto **dst, const auto &vec) {
     using T = typename std::remove_reference<decltype(vec)>::type::value_type;
     B200_CHECK(cudaMalloc((void **)dst, std::max<size_t>(vec.size(), 1) * sizeof(T)));
@@ -445,16 +422,6 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   up(&tl.d_ktab, ktab);
   const std::vector<unsigned short> zmask = build_zmask();
   up(&tl.d_zmask, zmask);
-
-  // exp tables
-  B200_CHECK(cudaMalloc((void **)&tl.d_etab, std::max<size_t>(etab_len, 4) * sizeof(double)));
-  {
-    const size_t nthreads = (size_t)tt.size() * tl.P;
-    etab_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, s>>>(tl.d_ttasks, d_tasks, (int)tt.size(), tl.P,
-                                                                  h[0], h[1], h[2], tl.d_etab);
-  }
-  B200_CHECK(cudaGetLastError());
-  count_launch();
 
   // pairs: count, scan, fill
   const size_t nbuckets = nblocks * kLpBuckets * kNumClasses;
@@ -587,8 +554,8 @@ struct TiledArgs {
   int *counter;              // dynamic work distribution (zeroed before the launch)
   const unsigned char *ktab;
   const unsigned short *zmask;
-  const double *etab;        // rows of P doubles per (task, axis)
-  int P, max_nb;
+  const TTask *ttasks;       // (roff, zl2) per tiled task
+  int max_nb;
   int tt_first;              // first ttask of this class
   int coef_base, coef_stride;  // slot of ttask q: coef_base + (q - tt_first) * coef_stride
   double *coef;
@@ -769,14 +736,14 @@ extern __shared__ double tiled_smem[];
 // Per-lane constants of the pair loops.
 struct LaneCtx {
   const uint4 *__restrict__ pairs;
-  const double *__restrict__ etab;       // exp tables of the level
+  const double *__restrict__ ttasks;     // the level's TTask records, as doubles (10 per record)
+  int e2t_index;                         // 2^(j/64) table in tiled_smem, in doubles
   double *__restrict__ coef0;            // coef + coef_base
   const unsigned char *__restrict__ ktab;
   int zm_index;                          // plane-mask table (biased) in tiled_smem, in 16-bit units
   int ws_index;                          // this warp's scratch (two stages) in tiled_smem, in doubles
   double my_h;
   int my_axis, my_t;
-  int emul, eadd;                        // my table entry: 4 * (epack >> 5) + nbq * emul + eadd - o
   int klane;                             // lj * kKPitch + li
   unsigned sel;                          // left shift that moves my axis' byte of opk to the top
   int tt_first, coef_stride;
@@ -802,15 +769,14 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
   // ptxas 12.9 (-O1 and up) miscompiles "copy, then overwrite the source" rotations
   // of loaded values in the large high-lp loop bodies -- later pairs of a run then
   // see stale data (tests/test_b200_parity.py::test_multi_pair_items pins this).
-  double e_n, roff_n, c_n[NCL];
+  double zl2_n, roff_n, c_n[NCL];
   int o_n;
 #define B200_FETCH(R)                                                          \
   {                                                                            \
     o_n = top_byte(R.z, c.sel);                                                \
-    const unsigned base_ = (R.w >> 3) & ~3u;                                   \
-    const int ge_ = (int)(R.w & 31u) * c.emul + c.eadd - o_n;                  \
-    roff_n = __ldg(c.etab + (base_ + (unsigned)c.my_axis));                    \
-    e_n = __ldg(c.etab + (base_ + (unsigned)ge_));                             \
+    const double *t_ = c.ttasks + (size_t)R.x * (sizeof(TTask) / sizeof(double)); \
+    roff_n = __ldg(t_ + c.my_axis);                                            \
+    zl2_n = __ldg(t_ + 3);                                                     \
     if (COLLOCATE) {                                                           \
       const double *c_ = c.coef0 + ((R.x - (unsigned)c.tt_first) * (unsigned)c.coef_stride + (unsigned)lane); \
       _Pragma("unroll") for (int k = 0; k < NCL; k++)                          \
@@ -839,12 +805,14 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
     double *ws = tiled_smem + c.ws_index + stage;
     stage = STAGE - stage;
     {
+      // my table entry exp(-zetp x^2), computed here: no exp tables in HBM
       const double x = (double)(c.my_t - o_n) * c.my_h - roff_n;
+      const double e_x = exp_neg_tab(zl2_n, x, tiled_smem + c.e2t_index);
       double *row = ws + lane * PITCH;
       if constexpr (LP == 0) {
-        row[0] = e_n;
+        row[0] = e_x;
       } else {
-        double v0 = e_n;
+        double v0 = e_x;
 #pragma unroll
         for (int l = 0; l + 1 <= LP; l += 2) {
           const double v1 = v0 * x;
@@ -956,9 +924,12 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B2
   double *const smem = tiled_smem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int STAGE = stage_doubles(LPHI);
-  unsigned short *s_zm = (unsigned short *)(smem + (size_t)kTiledWarps * 2 * STAGE);
+  // shared memory: [per-warp scratch, two stages][2^(j/64), 64 doubles][plane-mask table]
+  unsigned short *s_zm = (unsigned short *)(smem + (size_t)kTiledWarps * 2 * STAGE + 64);
   for (int q = tid; q < kZmRows * kZmPitch / 2; q += kTiledThreads)
     ((unsigned *)s_zm)[q] = ((const unsigned *)A.zmask)[q];
+  if (tid < 64)
+    smem[(size_t)kTiledWarps * 2 * STAGE + tid] = exp2((double)tid * (1.0 / 64.0));
   __syncthreads();  // the only CTA-wide barrier
 
   LaneCtx c;
@@ -969,18 +940,17 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B2
   c.my_h = (my_axis == 0) ? A.hx : ((my_axis == 1) ? A.hy : A.hz);
   c.sel = (my_axis == 0) ? 24u : ((my_axis == 1) ? 16u : 0u);
   c.my_axis = my_axis;
-  c.etab = A.etab;
-  c.emul = 2 * my_axis + 1;                                  // axis * (2 nbq + 16) + nbq
-  c.eadd = 16 * my_axis + 4 + ((my_axis == 2) ? 15 : 7) + c.my_t;
+  c.ttasks = reinterpret_cast<const double *>(A.ttasks);
+  c.e2t_index = kTiledWarps * 2 * STAGE;
   c.coef0 = A.coef + A.coef_base;
   c.tt_first = A.tt_first, c.coef_stride = A.coef_stride;
   c.pairs = (const uint4 *)A.pairs;
   c.ktab = A.ktab;
   c.klane = c.lj * kKPitch + c.li;
   // Opaque to the compiler from here on: it would otherwise re-derive these per-lane
-  // constants from the thread index inside the pair loops (9 instructions for eadd alone).
-  asm volatile("" : "+r"(c.eadd), "+r"(c.klane), "+r"(c.sel));
-  c.zm_index = kTiledWarps * 2 * STAGE * 4 + kZmBias;
+  // constants from the thread index inside the pair loops.
+  asm volatile("" : "+r"(c.my_t), "+r"(c.klane), "+r"(c.sel));
+  c.zm_index = (kTiledWarps * 2 * STAGE + 64) * 4 + kZmBias;
   c.ws_index = warp * 2 * STAGE;
 
   // persistent warps: work items are handed out in spatial order
@@ -1042,7 +1012,7 @@ __global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B2
 }
 
 inline size_t tiled_smem_bytes(const int lphi) {
-  return (size_t)kTiledWarps * 2 * stage_doubles(lphi) * sizeof(double) +
+  return (size_t)kTiledWarps * 2 * stage_doubles(lphi) * sizeof(double) + 64 * sizeof(double) +
          (size_t)kZmRows * kZmPitch * sizeof(unsigned short);
 }
 
@@ -1072,7 +1042,7 @@ template <bool COLLOCATE> inline unsigned launch_tiled(TiledLevel &tl, const Gri
   TiledArgs A;
   A.pairs = tl.d_pairs;
   A.ktab = tl.d_ktab, A.zmask = tl.d_zmask;
-  A.etab = tl.d_etab, A.P = tl.P, A.max_nb = tl.max_nb;
+  A.ttasks = tl.d_ttasks, A.max_nb = tl.max_nb;
   A.coef = L.coef, A.grid = L.grid;
   A.nx = L.level.npts_local[0], A.ny = L.level.npts_local[1], A.nz = L.level.npts_local[2];
   A.hx = L.level.dh[0], A.hy = L.level.dh[4], A.hz = L.level.dh[8];

@@ -107,6 +107,23 @@ def rel_diff(test, ref) -> float:
     return float(np.max(np.abs(test - ref) / np.maximum(1.0, np.abs(ref))))
 
 
+def norm_rel_diff(test, ref) -> float:
+    """Norm-wise relative error ||test - ref||_2 / ||ref||_2 (north_star's "relative error",
+    beside the reference validator's element-wise |d| / max(1, |ref|) of `rel_diff`)."""
+    test, ref = np.asarray(test, dtype=np.float64).ravel(), np.asarray(ref, dtype=np.float64).ravel()
+    den = float(np.linalg.norm(ref))
+    if den == 0.0:
+        return float(np.linalg.norm(test))
+    return float(np.linalg.norm(test - ref)) / den
+
+
+def assert_parity(got, ref, tol: float, what: str = "") -> None:
+    """Both measures must hold: the reference validator's and the norm-wise relative one."""
+    e1, e2 = rel_diff(got, ref), norm_rel_diff(got, ref)
+    assert e1 < tol, f"{what}: |d|/max(1,|ref|) = {e1:.3e} >= {tol:g}"
+    assert e2 < tol, f"{what}: ||d||/||ref|| = {e2:.3e} >= {tol:g}"
+
+
 def dummy_task_list(lib, t: dict, cycles: int, cycles_per_block: int):
     """grid_replay.c:154-214 with distinct block offsets."""
     n1, n2 = t["n1"], t["n2"]

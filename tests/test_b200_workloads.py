@@ -9,7 +9,7 @@ import pytest
 from cp2k_b200.grid_api import GRID_BACKEND_CPU, OffloadBuffer
 from cp2k_b200 import rsgrid
 from cp2k_b200.workload import build_h2o_workload
-from replay import rel_diff
+from replay import assert_parity, rel_diff
 from synth import make_workload
 
 pytestmark = pytest.mark.gpu
@@ -126,10 +126,7 @@ def test_h2o256_full_against_reference_cpu_backend(b200, reference):
     pab = wl.random_pab(17)
     ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab, forces=True)
     got = _run(b200, wl, pab, forces=True)
-    for a, b in zip(got[0], ref[0]):
-        assert rel_diff(a, b) < 1e-10
-    assert rel_diff(got[1], ref[1]) < 1e-10
-    assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
+    _check_full(got, ref)
 
 
 def test_h2o64_molopt_subset_against_reference_cpu_backend(b200, reference):
@@ -162,6 +159,38 @@ def test_nonortho_water_metagga_forces_virial(b200, reference, func, tau):
     assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
 
 
+def _check_full(got, ref):
+    for lvl, (a, b) in enumerate(zip(got[0], ref[0])):
+        assert_parity(a, b, 1e-10, f"grid level {lvl}")
+    assert_parity(got[1], ref[1], 1e-10, "hab blocks")
+    assert_parity(got[2], ref[2], 1e-8, "forces")
+    assert_parity(got[3], ref[3], 1e-8, "virial")
+
+
+def test_h2o1024_full_against_reference_cpu_backend(b200, reference):
+    """BASELINE.json config 5 itself: H2O-1024, all 5.0 M tasks on (315/189/105/63)^3 grids, with
+    forces + virial -- every grid value and every H element against the unmodified reference CPU
+    backend (element-wise and norm-wise), not only the adjointness property."""
+    wl = build_h2o_workload("H2O-1024")
+    assert wl.ntasks > 4_000_000
+    pab = wl.random_pab(18)
+    ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab, forces=True)
+    got = _run(b200, wl, pab, forces=True)
+    _check_full(got, ref)
+
+
+@pytest.mark.parametrize("func,tau", [(100, False), (200, True)])
+def test_nonortho_water_full_metagga_forces_virial(b200, reference, func, tau):
+    """BASELINE.json config 4 at full size: every task of the 64-molecule triclinic cell
+    (general-cell path), density and tau collocation, integrate with forces + virial."""
+    wl = build_h2o_workload("H2O-64_nonortho")
+    assert not wl.orthorhombic and wl.ntasks > 300_000
+    pab = wl.random_pab(19)
+    ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab, forces=True, func=func, tau=tau)
+    got = _run(b200, wl, pab, forces=True, func=func, tau=tau)
+    _check_full(got, ref)
+
+
 def test_h2o64_full_against_reference_cpu_backend(b200, reference):
     """The complete H2O-64 task list (362 k tasks: hundreds of pairs per grid block,
     several work items per block) against the unmodified reference CPU backend."""
@@ -169,7 +198,4 @@ def test_h2o64_full_against_reference_cpu_backend(b200, reference):
     pab = wl.random_pab(16)
     ref = _run(reference.load_reference(GRID_BACKEND_CPU), wl, pab, forces=True)
     got = _run(b200, wl, pab, forces=True)
-    for a, b in zip(got[0], ref[0]):
-        assert rel_diff(a, b) < 1e-10
-    assert rel_diff(got[1], ref[1]) < 1e-10
-    assert rel_diff(got[2], ref[2]) < 1e-8 and rel_diff(got[3], ref[3]) < 1e-8
+    _check_full(got, ref)
