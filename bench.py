@@ -227,7 +227,7 @@ def bench_config(wl, args, extra=None):
                        + ("+forces" if args.forces else "") + ("+virial" if getattr(args, "virial", False) else ""),
            "ntasks": wl.ntasks, "nblocks": wl.nblocks, "natoms": wl.natoms,
            "l2": "per-step working set (task records + P/H blocks + grids > 0.5 GB) exceeds the 126 MB L2",
-           "parallelism": (f"z-slab rs_grids over {args.gpus} GPU(s), NCCL halo sum/fill"
+           "parallelism": (f"z-slab rs_grids over {args.gpus} GPU(s), NCCL halo sum/fill ({getattr(args, 'halo', 'library')})"
                            if getattr(args, "decomp", "blocks") == "slab" and args.gpus > 1 else
                            f"blocks/tasks split over {args.gpus} GPU(s), replicated grids, NCCL all-reduce")}
     if extra:
@@ -351,6 +351,9 @@ def main():
     ap.add_argument("--decomp", default="blocks", choices=["blocks", "slab"],
                     help="multi-GPU decomposition: matrix blocks + replicated grids + all-reduce (default), "
                          "or z-slab rs_grids + NCCL halo sum/fill (cp2k_b200/rsgrid.py)")
+    ap.add_argument("--halo", default="library", choices=["library", "torch"],
+                    help="with --decomp slab: the library's C-callable NCCL halo exchange (grid_b200_halo_sum / "
+                         "_fill, default) or the torch.distributed restatement in cp2k_b200/rsgrid.py")
     ap.add_argument("--slab-compact", action="store_true",
                     help="with --decomp slab: per-rank compacted P/H blocks + all-to-all owner reduction of H")
     args = ap.parse_args()
@@ -401,7 +404,7 @@ def main():
     lib.set_kernel_variant(args.variant)
 
     wl_full = build_h2o_workload(args.workload, basis=args.basis)
-    slab_levels, hab_exchange = None, None
+    slab_levels, hab_exchange, halo_comm = None, None, None
     if args.decomp == "slab" and world > 1:
         from cp2k_b200 import rsgrid
 
@@ -411,6 +414,7 @@ def main():
         # buffers hold its own blocks only and the partial H blocks are summed into their
         # owners with one all-to-all instead of an all-reduce of the whole H buffer
         hab_exchange = rsgrid.HabExchange(wl_full, slab_levels, rank, world) if args.slab_compact else None
+        halo_comm = rsgrid.HaloComm(lib, rank, world, dist) if args.halo == "library" else None
     else:
         wl = split_blocks(wl_full, world, rank)
     torch.cuda.synchronize()
@@ -449,8 +453,12 @@ def main():
         for lay, sl, g in zip(wl.layouts, slab_levels, gs):
             n = lay.npts_local
             t = g.device[: int(n[0]) * int(n[1]) * int(n[2])].view(int(n[2]), int(n[1]), int(n[0]))
-            rsgrid.halo_sum(t, sl, rank, world, dist)   # density: halos -> owners
-            rsgrid.halo_fill(t, sl, rank, world, dist)  # potential: owners -> halos
+            if halo_comm is not None:  # ncclSend/ncclRecv grouped per level + one add kernel, in the library
+                halo_comm.halo_sum(t, sl)
+                halo_comm.halo_fill(t, sl)
+            else:
+                rsgrid.halo_sum(t, sl, rank, world, dist)   # density: halos -> owners
+                rsgrid.halo_fill(t, sl, rank, world, dist)  # potential: owners -> halos
 
     def step_resident():
         tl.collocate(FUNC, pab, grids)

@@ -27,6 +27,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
+import ctypes as C
+
 import numpy as np
 
 from .grid_api import GridLayout
@@ -323,3 +325,87 @@ def owned_view(grid, sl: SlabLevel, rank: int):
         return grid
     lo, hi = sl.owned[rank]
     return grid[sl.border: sl.border + (hi - lo)]
+
+
+# ----------------------------------------------------------------------------
+# The C-callable halo exchange of the library (include/grid_b200.h:
+# grid_b200_halo_sum / grid_b200_halo_fill, NCCL send/recv grouped per level).
+# ----------------------------------------------------------------------------
+class _CSlab(C.Structure):
+    _fields_ = [("npts_global", C.c_int * 3), ("nranks", C.c_int), ("rank", C.c_int), ("border", C.c_int),
+                ("distributed", C.c_bool), ("owned_lo", C.POINTER(C.c_int)), ("owned_hi", C.POINTER(C.c_int))]
+
+
+def c_slab(sl: SlabLevel, rank: int, world: int):
+    """`grid_b200_slab` for one level; returns (struct, keep-alive arrays)."""
+    lo = np.ascontiguousarray([o[0] for o in sl.owned], dtype=np.int32)
+    hi = np.ascontiguousarray([o[1] for o in sl.owned], dtype=np.int32)
+    cs = _CSlab((C.c_int * 3)(*[int(x) for x in sl.npts_global]), int(world), int(rank), int(sl.border),
+                bool(sl.distributed), lo.ctypes.data_as(C.POINTER(C.c_int)), hi.ctypes.data_as(C.POINTER(C.c_int)))
+    return cs, (lo, hi)
+
+
+def c_halo_plan(lib, sl: SlabLevel, rank: int, world: int):
+    """The library's exchange plan for `rank` (no GPU needed): list of
+    (src, dst, a, b, [(k, d, m), ...])."""
+    f = lib.lib.grid_b200_halo_plan
+    f.restype = C.c_int
+    f.argtypes = [C.POINTER(_CSlab), C.POINTER(C.c_int), C.c_int]
+    cs, keep = c_slab(sl, rank, world)
+    n = f(C.byref(cs), None, 0)
+    out = np.zeros(11 * max(n, 1), dtype=np.int32)
+    f(C.byref(cs), out.ctypes.data_as(C.POINTER(C.c_int)), n)
+    msgs = []
+    for i in range(n):
+        o = out[11 * i: 11 * i + 11]
+        msgs.append((int(o[0]), int(o[1]), int(o[2]), int(o[3]),
+                     [(int(o[5 + 3 * r]), int(o[6 + 3 * r]), int(o[7 + 3 * r])) for r in range(int(o[4]))]))
+    return msgs
+
+
+class HaloComm:
+    """An NCCL communicator of the library (`grid_b200_comm`) for the ranks of a
+    torch.distributed job: rank 0 draws the unique id, torch.distributed carries it."""
+
+    def __init__(self, lib, rank: int, world: int, dist, stream_ptr: int = 0):
+        import torch
+
+        L = lib.lib
+        L.grid_b200_comm_unique_id.restype = None
+        L.grid_b200_comm_unique_id.argtypes = [C.c_void_p]
+        L.grid_b200_comm_create.restype = None
+        L.grid_b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.grid_b200_comm_destroy.restype = None
+        L.grid_b200_comm_destroy.argtypes = [C.c_void_p]
+        for name in ("grid_b200_halo_sum", "grid_b200_halo_fill"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [C.c_void_p, C.POINTER(_CSlab), C.c_void_p]
+        self.L, self.rank, self.world = L, rank, world
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            L.grid_b200_comm_unique_id(uid.ctypes.data_as(C.c_void_p))
+        t = torch.from_numpy(uid).cuda()
+        dist.broadcast(t, 0)
+        uid = t.cpu().numpy()
+        self.handle = C.c_void_p()
+        L.grid_b200_comm_create(world, rank, uid.ctypes.data_as(C.c_void_p), C.c_void_p(stream_ptr), C.byref(self.handle))
+        self._slabs = {}
+
+    def _slab(self, sl: SlabLevel):
+        key = id(sl)
+        if key not in self._slabs:
+            self._slabs[key] = c_slab(sl, self.rank, self.world)
+        return self._slabs[key][0]
+
+    def halo_sum(self, grid, sl: SlabLevel) -> None:
+        """`grid`: this rank's local grid of the level, a contiguous CUDA float64 tensor."""
+        self.L.grid_b200_halo_sum(self.handle, C.byref(self._slab(sl)), C.c_void_p(grid.data_ptr()))
+
+    def halo_fill(self, grid, sl: SlabLevel) -> None:
+        self.L.grid_b200_halo_fill(self.handle, C.byref(self._slab(sl)), C.c_void_p(grid.data_ptr()))
+
+    def destroy(self) -> None:
+        if self.handle:
+            self.L.grid_b200_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+

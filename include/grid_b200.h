@@ -154,6 +154,44 @@ void grid_b200_integrate_pgf_products(
     const int *border_width, const double *grid, double *const *hab,
     const double *const *pab, double *forces);
 
+/* ---- z-slab distributed grids: halo exchange over NCCL ------------------------
+ *
+ * The rs_grid distribution restricted to 1-D z-slabs (src/pw/realspace_grid_types.F:413-415,
+ * 514-519): rank r owns the global planes [owned_lo[r], owned_hi[r]) of a level and keeps
+ * `border` halo planes on either side; its local grid is [owned + 2 border][ny][nx], the
+ * `npts_local` / `shift_local` / `border_width` it hands to grid_b200_create_task_list.
+ * grid_b200_halo_sum replaces the halo part of transfer_rs2pw_distributed
+ * (realspace_grid_types.F:988-1204): after collocate every rank's halo planes are ADDED into
+ * the planes of their owners (and zeroed).  grid_b200_halo_fill replaces that of
+ * transfer_pw2rs_distributed (:1677-1893): before integrate the owners' planes are COPIED
+ * into every halo.  Levels with distributed == false are replicated: the sum is an all-reduce
+ * (:763-825), the fill does nothing.  `grid_dev` is device memory; the calls enqueue on the
+ * communicator's stream and return (one grouped NCCL send/recv per level plus one add kernel).
+ *
+ * A communicator wraps ncclCommInitRank: one rank obtains the 128-byte unique id
+ * (grid_b200_comm_unique_id) and hands it to the others -- in CP2K over the MPI communicator
+ * of the rs_grid (mp_bcast), in the Python harness over torch.distributed. */
+typedef struct grid_b200_comm grid_b200_comm;
+typedef struct {
+  int npts_global[3];
+  int nranks, rank;
+  int border;          /* halo planes on either side */
+  bool distributed;    /* false: replicated level */
+  const int *owned_lo; /* [nranks] */
+  const int *owned_hi; /* [nranks] */
+} grid_b200_slab;
+
+void grid_b200_comm_unique_id(void *out128);
+void grid_b200_comm_create(const int nranks, const int rank, const void *unique_id128, void *cuda_stream,
+                           grid_b200_comm **comm_out);
+void grid_b200_comm_destroy(grid_b200_comm *comm);
+void grid_b200_halo_sum(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev);
+void grid_b200_halo_fill(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev);
+/* The messages `slab->rank` takes part in, 11 ints each {src, dst, first, last+1 halo plane on
+ * src, nruns, then per run: offset in the message, first owned local plane on dst, planes};
+ * returns their number (needs no GPU: used to test the plan). */
+int grid_b200_halo_plan(const grid_b200_slab *slab, int *out, const int max_msgs);
+
 /* ---- backend controls (no counterpart in the reference) ------------------ */
 
 /* Device selection follows offload_get_chosen_device()

@@ -108,3 +108,25 @@ def test_plans_are_cached_and_consistent():
     for r in range(8):
         sends, _ = rsgrid._rank_plan(sl, r, 8)
         assert sum(b - a for _, a, b in sends) == 2 * sl.border
+
+
+def test_library_halo_plan_matches_python_plan():
+    """The C-callable halo exchange (grid_b200_halo_sum / _fill) derives its message plan in
+    the library; it must be the plan of cp2k_b200.rsgrid (which the gloo tests verify against
+    a full-grid reference): same messages in the same order, same owned runs."""
+    from cp2k_b200 import rsgrid
+    from cp2k_b200.grid_api import load_b200
+
+    lib = load_b200()
+    for nz, world, border in ((80, 2, 9), (72, 6, 14), (126, 8, 20), (200, 8, 21), (40, 3, 5)):
+        owned = [rsgrid.get_limit(nz, world, r) for r in range(world)]
+        sl = rsgrid.SlabLevel(True, np.array([10, 12, nz]), border, owned)
+        if max(hi - lo for lo, hi in owned) + 2 * border > nz:
+            continue
+        for rank in range(world):
+            sends, recvs = rsgrid._rank_plan(sl, rank, world)
+            msgs = rsgrid.c_halo_plan(lib, sl, rank, world)
+            c_sends = [(dst, a, b) for (src, dst, a, b, runs) in msgs if src == rank]
+            c_recvs = [(src, b - a, runs) for (src, dst, a, b, runs) in msgs if dst == rank]
+            assert c_sends == [(int(p), int(a), int(b)) for p, a, b in sends]
+            assert c_recvs == [(int(p), int(n), [tuple(int(x) for x in r) for r in runs]) for p, n, runs in recvs]
