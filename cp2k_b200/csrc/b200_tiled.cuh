@@ -769,16 +769,14 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
   // ptxas 12.9 (-O1 and up) miscompiles "copy, then overwrite the source" rotations
   // of loaded values in the large high-lp loop bodies -- later pairs of a run then
   // see stale data (tests/test_b200_parity.py::test_multi_pair_items pins this).
-  double e_n, roff_n, c_n[NCL];
+  double zl2_n, roff_n, c_n[NCL];
   int o_n;
-  // (the next pair's table entry exp(-zetp x^2) is COMPUTED here, one pair ahead: its
-  // dependent chain overlaps the current pair's plane loop; no exp tables in HBM)
 #define B200_FETCH(R)                                                          \
   {                                                                            \
     o_n = top_byte(R.z, c.sel);                                                \
     const double *t_ = c.ttasks + (size_t)R.x * (sizeof(TTask) / sizeof(double)); \
     roff_n = __ldg(t_ + c.my_axis);                                            \
-    e_n = exp_neg_tab(__ldg(t_ + 3), (double)(c.my_t - o_n) * c.my_h - roff_n, tiled_smem + c.e2t_index); \
+    zl2_n = __ldg(t_ + 3);                                                     \
     if (COLLOCATE) {                                                           \
       const double *c_ = c.coef0 + ((R.x - (unsigned)c.tt_first) * (unsigned)c.coef_stride + (unsigned)lane); \
       _Pragma("unroll") for (int k = 0; k < NCL; k++)                          \
@@ -807,12 +805,16 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
     double *ws = tiled_smem + c.ws_index + stage;
     stage = STAGE - stage;
     {
+      // my table entry exp(-zetp x^2), computed here: no exp tables in HBM.  (Computing it
+      // one pair ahead, in the fetch stage, was measured slower: 9.0 / 11.6 ms against
+      // 8.1 / 10.5 ms per H2O-256 collocate / integrate.)
       const double x = (double)(c.my_t - o_n) * c.my_h - roff_n;
+      const double e_x = exp_neg_tab(zl2_n, x, tiled_smem + c.e2t_index);
       double *row = ws + lane * PITCH;
       if constexpr (LP == 0) {
-        row[0] = e_n;
+        row[0] = e_x;
       } else {
-        double v0 = e_n;
+        double v0 = e_x;
 #pragma unroll
         for (int l = 0; l + 1 <= LP; l += 2) {
           const double v1 = v0 * x;
