@@ -572,6 +572,26 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_ms = float(dt.item()) / n_e2e * 1e3
+    # The same definition at every N ("host P in -> host H out, grids wherever the mode keeps
+    # them"): at N = 1 also measured with the grids resident, like the N > 1 arm does.
+    e2e_ph_ms = None
+    if world == 1:
+        lib.set_device_resident(True)
+        pin_pab1 = torch.from_numpy(pab_h.host).pin_memory()
+        pin_hab1 = torch.empty(wl.pab_len, dtype=torch.float64).pin_memory()
+
+        def step_ph():
+            pab.device.copy_(pin_pab1, non_blocking=True)
+            tl.collocate(FUNC, pab, grids)
+            tl.integrate(TAU, pab if args.forces else None, grids, hab, forces, virial)
+            pin_hab1.copy_(hab.device[: wl.pab_len], non_blocking=True)
+            torch.cuda.synchronize()
+
+        step_ph()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            step_ph()
+        e2e_ph_ms = (time.perf_counter() - t0) / n_e2e * 1e3
     if world == 1:
         h2d = 8 * wl.pab_len * (2 if args.forces else 1) + int(grid_bytes)
         d2h = int(grid_bytes) + 8 * wl.pab_len
@@ -670,7 +690,10 @@ def main():
                                                          "task_block_pairs": st["npairs"]}),
             "clocks": clocks,
             "e2e": {"value": flops_total / (e2e_ms * 1e-3) * 1e-9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+                    "what": ("host buffers through the public API: P blocks and grids in, grids and H blocks out"
+                             if world == 1 else "this rank's P blocks in, its H blocks out, grids stay on the device"),
+                    "ms_per_step_p_in_h_out_grids_resident": e2e_ph_ms if world == 1 else e2e_ms},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu,
             "multi_gpu_parity": parity,

@@ -267,8 +267,17 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
   cl.max_lp0 = max_lp0, cl.max_n = max_n, cl.max_nb = max_nb;
   if (tt.empty())
     return;
-  std::stable_sort(tt.begin(), tt.end(),
-                   [](const TTask &a, const TTask &b) { return lp_class(a.lp0) < lp_class(b.lp0); });
+  {  // stable partition by lp class (three classes: one counting pass instead of a sort)
+    std::vector<TTask> sorted(tt.size());
+    size_t pos[kNumClasses + 1] = {0, 0, 0, 0};
+    for (const TTask &X : tt)
+      pos[lp_class(X.lp0) + 1]++;
+    for (int c = 0; c < kNumClasses; c++)
+      pos[c + 1] += pos[c];
+    for (const TTask &X : tt)
+      sorted[pos[lp_class(X.lp0)]++] = X;
+    tt.swap(sorted);
+  }
   cl.h_tt_task.resize(tt.size());
   for (int c = 0; c <= kNumClasses; c++)
     cl.class_tt_first[c] = 0;

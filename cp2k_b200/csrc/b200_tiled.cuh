@@ -37,6 +37,7 @@
 //     memory is double buffered (one __syncwarp per pair).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -342,9 +343,28 @@ template <int PASS> __global__ void pairgen_kernel(const PairGenArgs A) {
 // ---------------------------------------------------------------------------
 // Host: per-level build.
 // ---------------------------------------------------------------------------
+// GRID_B200_CREATE_TIMING=1: wall time of the builder's phases on stderr
+struct CreateTimer {
+  bool on;
+  cudaStream_t s;
+  std::chrono::steady_clock::time_point t;
+  CreateTimer(cudaStream_t stream) : on(getenv("GRID_B200_CREATE_TIMING") != nullptr), s(stream) {
+    t = std::chrono::steady_clock::now();
+  }
+  void tick(const char *what) {
+    if (!on)
+      return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "grid_b200 create:   %-26s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vector<TaskDev> &tasks,
                               const TaskDev *d_tasks, const int first, const int last,
                               std::vector<int> &generic_ids, cudaStream_t s) {
+  CreateTimer tm(s);
   tl.release();
   const double h[3] = {L.dh[0], L.dh[4], L.dh[8]};
   const double drmin = fmin(h[0], fmin(h[1], h[2]));
@@ -388,11 +408,21 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   tl.max_lp0 = max_lp0;
   tl.max_n = max_n;
   tl.max_nb = max_nb;
+  tm.tick("level: select tasks");
   if (tt.empty())
     return;
   // class-sorted: a task's coefficient slot is then pure arithmetic on its index
-  std::stable_sort(tt.begin(), tt.end(),
-                   [](const TTask &a, const TTask &b) { return lp_class(a.lp0) < lp_class(b.lp0); });
+  {  // stable partition by lp class (three classes: one counting pass instead of a sort)
+    std::vector<TTask> sorted(tt.size());
+    size_t pos[kNumClasses + 1] = {0, 0, 0, 0};
+    for (const TTask &X : tt)
+      pos[lp_class(X.lp0) + 1]++;
+    for (int c = 0; c < kNumClasses; c++)
+      pos[c + 1] += pos[c];
+    for (const TTask &X : tt)
+      sorted[pos[lp_class(X.lp0)]++] = X;
+    tt.swap(sorted);
+  }
   tl.h_tt_task.resize(tt.size());
   for (int c = 0; c <= kNumClasses; c++)
     tl.class_tt_first[c] = 0;
@@ -417,11 +447,13 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
     if (!vec.empty())
       B200_CHECK(cudaMemcpyAsync(*dst, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   };
+  tm.tick("level: class sort, K tables");
   up(&tl.d_ttasks, tt);
   up(&tl.d_khead, heads);
   up(&tl.d_ktab, ktab);
   const std::vector<unsigned short> zmask = build_zmask();
   up(&tl.d_zmask, zmask);
+  tm.tick("level: uploads");
 
   // pairs: count, scan, fill
   const size_t nbuckets = nblocks * kLpBuckets * kNumClasses;
@@ -450,6 +482,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
                              cudaMemcpyDeviceToHost, s));
   B200_CHECK(cudaStreamSynchronize(s));
   const size_t npairs = start[nbuckets];
+  tm.tick("level: count pairs, scan");
   B200_ASSERT(npairs < ((size_t)1 << 31), "too many (task, block) pairs on one level");
   tl.npairs = (long long)npairs;
   B200_CHECK(cudaMalloc((void **)&tl.d_pairs, (npairs + kPairPad) * sizeof(TPair)));
@@ -493,6 +526,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
       B200_CHECK(cudaMemcpyAsync(tl.d_pairs + npairs + i, tl.d_pairs + npairs - 1, sizeof(TPair),
                                  cudaMemcpyDeviceToDevice, s));
 
+  tm.tick("level: fill + sort pairs");
   // work items per lp class: a block's pairs of that class (contiguous, ordered by lp) cut into chunks
   std::vector<TWork> work;
   const size_t target_items = (size_t)148 * 64;
@@ -537,6 +571,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
   B200_CHECK(cudaMalloc((void **)&tl.d_counters, 2 * kNumClasses * 4 * sizeof(int)));
   B200_CHECK(cudaStreamSynchronize(s));
   cudaFree(d_temp), cudaFree(d_count), cudaFree(d_start);
+  tm.tick("level: work items");
 }
 
 inline bool tiled_supports(const TiledLevel &tl, const int max_lp) {

@@ -11,11 +11,13 @@
 // __constant__ tables are shared.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <parallel/algorithm>
 #include <vector>
 
 #include "b200_internal.cuh"
@@ -452,6 +454,18 @@ static void build_task_list(
     const int *npts_global, const int *npts_local, const int *shift_local,
     const int *border_width, const double *dh, const double *dh_inv) {
   cudaStream_t s = g_stream;
+  // GRID_B200_CREATE_TIMING=1: wall time of the builder's phases on stderr
+  static const bool timing = (getenv("GRID_B200_CREATE_TIMING") != nullptr);
+  auto t_last = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!timing)
+      return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "grid_b200 create: %-28s %8.1f ms\n", what,
+            std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   tl.path = (nlevels > kCtMaxLevels) ? 2 : variant_path();
   tl.ortho = orthorhombic;
   tl.ntasks = ntasks, tl.nlevels = nlevels, tl.natoms = natoms;
@@ -499,7 +513,8 @@ static void build_task_list(
   // sort like the reference: (level, block, iset, jset), stable
   std::vector<int> order(ntasks);
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+  // (multi-threaded: the list has 10^6 - 10^7 tasks and is rebuilt every MD step)
+  __gnu_parallel::stable_sort(order.begin(), order.end(), [&](int a, int b) {
     if (level_list[a] != level_list[b])
       return level_list[a] < level_list[b];
     if (block_num_list[a] != block_num_list[b])
@@ -509,6 +524,7 @@ static void build_task_list(
     return jset_list[a] < jset_list[b];
   });
 
+  tick("basis sets, task sort");
   tl.h_tasks.resize(ntasks);
 #pragma omp parallel for schedule(static)
   for (int it = 0; it < ntasks; it++) {
@@ -600,6 +616,7 @@ static void build_task_list(
     }
   }
 
+  tick("task records (host)");
   // per-level ranges and maxima
   for (int l = 0; l < nlevels; l++)
     tl.linfo[l].first = tl.linfo[l].last = 0;
@@ -640,7 +657,9 @@ static void build_task_list(
     if (tl.linfo[l].last == 0)
       tl.linfo[l].first = 0;
 
+  tick("level ranges, maxima");
   tl.d_tasks.upload(tl.h_tasks, s);
+  tick("task records upload");
   std::vector<int> iota(ntasks);
   std::iota(iota.begin(), iota.end(), 0);
   tl.d_iota.upload(iota, s);
@@ -648,7 +667,7 @@ static void build_task_list(
   // tasks grouped by matrix block for the hab/forces kernel
   std::vector<int> by_block(ntasks);
   std::iota(by_block.begin(), by_block.end(), 0);
-  std::stable_sort(by_block.begin(), by_block.end(), [&](int a, int b) {
+  __gnu_parallel::stable_sort(by_block.begin(), by_block.end(), [&](int a, int b) {
     const TaskDev &A = tl.h_tasks[a], &B = tl.h_tasks[b];
     if (A.block_num != B.block_num)
       return A.block_num < B.block_num;
@@ -704,6 +723,7 @@ static void build_task_list(
       B200_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
 
+  tick("block order, size classes");
   tl.h_Tptrs.assign((size_t)nlevels * (kMaxLp + 1), nullptr);
   tl.d_Tptrs.upload(tl.h_Tptrs, s);
   tl.d_grids.resize(nlevels);
@@ -726,6 +746,7 @@ static void build_task_list(
     tl.generic_first[l] = (int)tl.h_generic_ids.size();
     tl.h_generic_ids.insert(tl.h_generic_ids.end(), generic_ids.begin(), generic_ids.end());
   }
+  tick("tiled levels (pairs)");
   tl.generic_first[nlevels] = (int)tl.h_generic_ids.size();
   tl.d_generic_ids.upload(tl.h_generic_ids, s);
   if (tl.path == 0) {
