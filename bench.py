@@ -450,12 +450,18 @@ def main():
             for g in gs:
                 dist.all_reduce(g.device)
             return
+        if halo_comm is not None:
+            # the library's exchange: ONE grouped NCCL send/recv (+ all-reduce of the replicated
+            # levels) for the sum of all levels, the add kernels, one more group for the fill
+            ts = [g.device for g in gs]
+            halo_comm.halo_sum_levels(ts, slab_levels)
+            halo_comm.halo_fill_levels(ts, slab_levels)
+            return
         for lay, sl, g in zip(wl.layouts, slab_levels, gs):
             n = lay.npts_local
             t = g.device[: int(n[0]) * int(n[1]) * int(n[2])].view(int(n[2]), int(n[1]), int(n[0]))
-            if halo_comm is not None:  # ncclSend/ncclRecv grouped per level + one add kernel, in the library
-                halo_comm.halo_sum(t, sl)
-                halo_comm.halo_fill(t, sl)
+            if False:
+                pass
             else:
                 rsgrid.halo_sum(t, sl, rank, world, dist)   # density: halos -> owners
                 rsgrid.halo_fill(t, sl, rank, world, dist)  # potential: owners -> halos
@@ -697,6 +703,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_gpu": reference_gpu,
             "multi_gpu_parity": parity,
+            # what the step spends outside this rank's kernels (rank 0's view): the grid exchange
+            # (all-reduce, or halo sum + fill) and the owner reduction of H
+            "exchange_ms_per_step": (ms_per_step - sum(v[0] for v in tm.values()) / args.steps) if world > 1 else 0.0,
             "create_task_list": {"ms": create_ms, "device_bytes": int(table_bytes),
                                  "in_steps": create_ms / ms_per_step},
         }

@@ -74,6 +74,11 @@ struct ScopedTimer {
     if (!on)
       return;
     B200_CHECK(cudaEventRecord(sp.b, s));
+    if (g_spans.size() >= 65536) {  // nobody drains the timers: drop the oldest span
+      cudaEventDestroy(g_spans.front().a);
+      cudaEventDestroy(g_spans.front().b);
+      g_spans.erase(g_spans.begin());
+    }
     g_spans.push_back(sp);
   }
 };
@@ -83,7 +88,8 @@ static void activate_device() {
     B200_CHECK(cudaSetDevice(g_device));
   int dev = 0;
   B200_CHECK(cudaGetDevice(&dev));
-  if (dev < 64 && !g_tables_uploaded[dev]) {
+  B200_ASSERT(dev >= 0 && dev < 64, "device index beyond the constant-table bookkeeping (64 devices)");
+  if (!g_tables_uploaded[dev]) {
     OrbTable tab;
     memset(&tab, 0, sizeof(tab));
     for (int lx = 0; lx <= 15; lx++)

@@ -212,22 +212,26 @@ int grid_b200_halo_plan(const grid_b200_slab *slab, int *out, const int max_msgs
   return n;
 }
 
-void grid_b200_halo_sum(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev) {
+// All levels of a call in ONE grouped NCCL operation (the launch latency of a group, not the
+// NVLink transfer, is what a level's exchange costs): halo planes to their owners for the
+// distributed levels, an all-reduce for the replicated ones; then the adds and the halo reset.
+void grid_b200_halo_sum_levels(grid_b200_comm *comm, const int nlevels, const grid_b200_slab *const *slabs,
+                               double *const *grids_dev) {
   HaloComm &H = *(HaloComm *)comm;
-  const grid_b200_slab &S = *slab;
-  check_slab(H, S);
   cudaStream_t s = H.stream;
-  const size_t plane = (size_t)S.npts_global[0] * S.npts_global[1];
-  if (!S.distributed) {  // replicated level: every rank holds the whole grid
-    if (H.nranks > 1)
-      B200_NCCL(nccl().AllReduce(grid_dev, grid_dev, plane * S.npts_global[2], kNcclDouble, kNcclSum, H.comm, s));
-    return;
-  }
-  const std::vector<HaloMsg> plan = halo_plan(S);
+  std::vector<std::vector<HaloMsg>> plans(nlevels);
   size_t need = 0;
-  for (const HaloMsg &M : plan)
-    if (M.dst == S.rank)
-      need += (size_t)(M.b - M.a) * plane;
+  for (int l = 0; l < nlevels; l++) {
+    const grid_b200_slab &S = *slabs[l];
+    check_slab(H, S);
+    if (!S.distributed)
+      continue;
+    plans[l] = halo_plan(S);
+    const size_t plane = (size_t)S.npts_global[0] * S.npts_global[1];
+    for (const HaloMsg &M : plans[l])
+      if (M.dst == S.rank)
+        need += (size_t)(M.b - M.a) * plane;
+  }
   if (need > H.tmp_cap) {
     cudaFree(H.tmp);
     B200_CHECK(cudaMalloc((void **)&H.tmp, need * sizeof(double)));
@@ -235,57 +239,89 @@ void grid_b200_halo_sum(grid_b200_comm *comm, const grid_b200_slab *slab, double
   }
   B200_NCCL(nccl().GroupStart());
   size_t off = 0;
-  for (const HaloMsg &M : plan) {
-    const size_t cnt = (size_t)(M.b - M.a) * plane;
-    if (M.src == S.rank)
-      B200_NCCL(nccl().Send(grid_dev + (size_t)M.a * plane, cnt, kNcclDouble, M.dst, H.comm, s));
-    if (M.dst == S.rank) {
-      B200_NCCL(nccl().Recv(H.tmp + off, cnt, kNcclDouble, M.src, H.comm, s));
-      off += cnt;
+  for (int l = 0; l < nlevels; l++) {
+    const grid_b200_slab &S = *slabs[l];
+    const size_t plane = (size_t)S.npts_global[0] * S.npts_global[1];
+    if (!S.distributed) {  // replicated level: every rank holds the whole grid
+      if (H.nranks > 1)
+        B200_NCCL(nccl().AllReduce(grids_dev[l], grids_dev[l], plane * S.npts_global[2], kNcclDouble, kNcclSum,
+                                   H.comm, s));
+      continue;
+    }
+    for (const HaloMsg &M : plans[l]) {
+      const size_t cnt = (size_t)(M.b - M.a) * plane;
+      if (M.src == S.rank)
+        B200_NCCL(nccl().Send(grids_dev[l] + (size_t)M.a * plane, cnt, kNcclDouble, M.dst, H.comm, s));
+      if (M.dst == S.rank) {
+        B200_NCCL(nccl().Recv(H.tmp + off, cnt, kNcclDouble, M.src, H.comm, s));
+        off += cnt;
+      }
     }
   }
   B200_NCCL(nccl().GroupEnd());
   off = 0;
-  for (const HaloMsg &M : plan) {
-    if (M.dst != S.rank)
+  for (int l = 0; l < nlevels; l++) {
+    const grid_b200_slab &S = *slabs[l];
+    if (!S.distributed)
       continue;
-    for (const HaloRun &R : M.runs) {
-      const size_t n = (size_t)R.m * plane;
-      halo_add_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(
-          grid_dev + (size_t)R.d * plane, H.tmp + off + (size_t)R.k * plane, n);
-      count_launch();
+    const size_t plane = (size_t)S.npts_global[0] * S.npts_global[1];
+    for (const HaloMsg &M : plans[l]) {
+      if (M.dst != S.rank)
+        continue;
+      for (const HaloRun &R : M.runs) {
+        const size_t n = (size_t)R.m * plane;
+        halo_add_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, s>>>(
+            grids_dev[l] + (size_t)R.d * plane, H.tmp + off + (size_t)R.k * plane, n);
+        count_launch();
+      }
+      off += (size_t)(M.b - M.a) * plane;
     }
-    off += (size_t)(M.b - M.a) * plane;
+    // the halo has been handed over: zero it, so that a later sum is idempotent
+    const int nown = S.owned_hi[S.rank] - S.owned_lo[S.rank];
+    B200_CHECK(cudaMemsetAsync(grids_dev[l], 0, (size_t)S.border * plane * sizeof(double), s));
+    B200_CHECK(cudaMemsetAsync(grids_dev[l] + (size_t)(S.border + nown) * plane, 0,
+                               (size_t)S.border * plane * sizeof(double), s));
   }
   B200_CHECK(cudaGetLastError());
-  // the halo has been handed over: zero it, so that a later sum is idempotent
-  const int nown = S.owned_hi[S.rank] - S.owned_lo[S.rank];
-  B200_CHECK(cudaMemsetAsync(grid_dev, 0, (size_t)S.border * plane * sizeof(double), s));
-  B200_CHECK(cudaMemsetAsync(grid_dev + (size_t)(S.border + nown) * plane, 0, (size_t)S.border * plane * sizeof(double), s));
+}
+
+void grid_b200_halo_sum(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev) {
+  grid_b200_halo_sum_levels(comm, 1, &slab, &grid_dev);
+}
+
+// The halo sum's plan run backwards: owners send their runs, halo holders receive them straight
+// into the halo planes -- no staging buffer, no kernel; all levels in one grouped operation.
+void grid_b200_halo_fill_levels(grid_b200_comm *comm, const int nlevels, const grid_b200_slab *const *slabs,
+                                double *const *grids_dev) {
+  HaloComm &H = *(HaloComm *)comm;
+  cudaStream_t s = H.stream;
+  bool any = false;
+  for (int l = 0; l < nlevels; l++) {
+    check_slab(H, *slabs[l]);
+    any = any || slabs[l]->distributed;
+  }
+  if (!any)
+    return;
+  B200_NCCL(nccl().GroupStart());
+  for (int l = 0; l < nlevels; l++) {
+    const grid_b200_slab &S = *slabs[l];
+    if (!S.distributed)
+      continue;
+    const size_t plane = (size_t)S.npts_global[0] * S.npts_global[1];
+    for (const HaloMsg &M : halo_plan(S))
+      for (const HaloRun &R : M.runs) {
+        const size_t cnt = (size_t)R.m * plane;
+        if (M.dst == S.rank)
+          B200_NCCL(nccl().Send(grids_dev[l] + (size_t)R.d * plane, cnt, kNcclDouble, M.src, H.comm, s));
+        if (M.src == S.rank)
+          B200_NCCL(nccl().Recv(grids_dev[l] + (size_t)(M.a + R.k) * plane, cnt, kNcclDouble, M.dst, H.comm, s));
+      }
+  }
+  B200_NCCL(nccl().GroupEnd());
 }
 
 void grid_b200_halo_fill(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev) {
-  HaloComm &H = *(HaloComm *)comm;
-  const grid_b200_slab &S = *slab;
-  check_slab(H, S);
-  if (!S.distributed)
-    return;
-  cudaStream_t s = H.stream;
-  const size_t plane = (size_t)S.npts_global[0] * S.npts_global[1];
-  const std::vector<HaloMsg> plan = halo_plan(S);
-  // the halo sum's plan run backwards: owners send their runs, halo holders receive them
-  // straight into the halo planes -- no staging buffer, no kernel
-  B200_NCCL(nccl().GroupStart());
-  for (const HaloMsg &M : plan) {
-    for (const HaloRun &R : M.runs) {
-      const size_t cnt = (size_t)R.m * plane;
-      if (M.dst == S.rank)
-        B200_NCCL(nccl().Send(grid_dev + (size_t)R.d * plane, cnt, kNcclDouble, M.src, H.comm, s));
-      if (M.src == S.rank)
-        B200_NCCL(nccl().Recv(grid_dev + (size_t)(M.a + R.k) * plane, cnt, kNcclDouble, M.dst, H.comm, s));
-    }
-  }
-  B200_NCCL(nccl().GroupEnd());
+  grid_b200_halo_fill_levels(comm, 1, &slab, &grid_dev);
 }
 
 }  // extern "C"

@@ -404,6 +404,25 @@ class HaloComm:
     def halo_fill(self, grid, sl: SlabLevel) -> None:
         self.L.grid_b200_halo_fill(self.handle, C.byref(self._slab(sl)), C.c_void_p(grid.data_ptr()))
 
+    def _arrays(self, grids, levels):
+        n = len(levels)
+        slabs = (C.POINTER(_CSlab) * n)(*[C.pointer(self._slab(sl)) for sl in levels])
+        ptrs = (C.c_void_p * n)(*[g.data_ptr() for g in grids])
+        return n, slabs, ptrs
+
+    def halo_sum_levels(self, grids, levels) -> None:
+        """All levels in one grouped NCCL operation (`grids`: the local CUDA tensors per level)."""
+        f = self.L.grid_b200_halo_sum_levels
+        f.restype, f.argtypes = None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        n, slabs, ptrs = self._arrays(grids, levels)
+        f(self.handle, n, slabs, ptrs)
+
+    def halo_fill_levels(self, grids, levels) -> None:
+        f = self.L.grid_b200_halo_fill_levels
+        f.restype, f.argtypes = None, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        n, slabs, ptrs = self._arrays(grids, levels)
+        f(self.handle, n, slabs, ptrs)
+
     def destroy(self) -> None:
         if self.handle:
             self.L.grid_b200_comm_destroy(self.handle)

@@ -187,6 +187,12 @@ void grid_b200_comm_create(const int nranks, const int rank, const void *unique_
 void grid_b200_comm_destroy(grid_b200_comm *comm);
 void grid_b200_halo_sum(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev);
 void grid_b200_halo_fill(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev);
+/* All levels of a call in one grouped NCCL operation (what a level's exchange costs is the
+ * launch latency of a group, not the NVLink transfer). */
+void grid_b200_halo_sum_levels(grid_b200_comm *comm, const int nlevels, const grid_b200_slab *const *slabs,
+                               double *const *grids_dev);
+void grid_b200_halo_fill_levels(grid_b200_comm *comm, const int nlevels, const grid_b200_slab *const *slabs,
+                                double *const *grids_dev);
 /* The messages `slab->rank` takes part in, 11 ints each {src, dst, first, last+1 halo plane on
  * src, nruns, then per run: offset in the message, first owned local plane on dst, planes};
  * returns their number (needs no GPU: used to test the plan). */
