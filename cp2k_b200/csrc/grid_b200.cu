@@ -218,6 +218,7 @@ struct TaskList {
   std::vector<cudaEvent_t> ev_join;
   double stats[16] = {0};
   bool stats_ready = false;
+  int last_dl = 0;                   // l growth of the last collocate / integrate call (statistics)
   int path = 0;                      // which tiled family the list was built for (0 / 2)
   CtileList ct;
 
@@ -902,6 +903,7 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   }
   B200_ASSERT(tl.nlevels == nlevels, "nlevels differs from the task list");
   const int dl = F.dla_max + F.dlb_max;
+  tl.last_dl = dl;
   ensure_coef_offsets(tl, dl, s);
   ensure_transforms(tl, dl, s);
   ensure_gather_lists(tl, F.dla_max, F.dlb_max, s);
@@ -1098,6 +1100,7 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   if (compute_tau)
     dla_max += 1, dlb_max += 1, dla_min -= 1, dlb_min -= 1;
   const int dl = dla_max + dlb_max;
+  tl.last_dl = dl;
   ensure_coef_offsets(tl, dl, s);
   ensure_transforms(tl, dl, s);
   ensure_gather_lists(tl, dla_max, dlb_max, s);
@@ -1274,6 +1277,23 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   // (hab not resident: its copy back to host_buffer must have landed on return)
   if (!g_device_resident || !hab_resident || do_f || do_v)
     B200_CHECK(cudaStreamSynchronize(s));
+}
+
+// Tasks per lp (la_max + lb_max plus the l growth of the list's last call), orthorhombic and
+// general path separately -- what gpu/grid_gpu_context.cu:538-552 forwards to
+// grid_library_counter_add after a call (the GRID STATISTICS table of a CP2K run).
+void grid_b200_get_task_counts(const grid_b200_task_list *ptr, int ortho[20], int general[20]) {
+  for (int i = 0; i < 20; i++)
+    ortho[i] = 0, general[i] = 0;
+  if (ptr == nullptr)
+    return;
+  const TaskList &tl = *(const TaskList *)ptr;
+  for (const TaskDev &T : tl.h_tasks) {
+    if (T.skip)
+      continue;
+    const int lp = std::min(T.la_max + T.lb_max + tl.last_dl, 19);
+    (T.use_ortho ? ortho : general)[lp]++;
+  }
 }
 
 int grid_b200_get_stats(const grid_b200_task_list *ptr, double *out, const int n) {

@@ -221,6 +221,12 @@ void grid_b200_set_device_resident(const bool flag);
  * cover all three. */
 void grid_b200_set_kernel_variant(const int variant);
 
+/* Tasks per lp (including the l growth of the list's last collocate / integrate call), for the
+ * orthorhombic and the general path: what the dispatcher arm forwards to
+ * grid_library_counter_add (src/grid/common/grid_library.c:135-147), like
+ * gpu/grid_gpu_context.cu:538-552 does. */
+void grid_b200_get_task_counts(const grid_b200_task_list *task_list, int ortho[20], int general[20]);
+
 /* Number of CUDA kernels launched by this library since load. */
 long long grid_b200_get_launch_count(void);
 

@@ -32,12 +32,24 @@ FREE_ARM = """
     task_list->b200 = NULL;
   }
 """
+COUNTERS = """
+    { /* GRID STATISTICS, as gpu/grid_gpu_context.cu:538-552 (host thread) */
+      int b200_ortho[20], b200_general[20];
+      grid_b200_get_task_counts(task_list->b200, b200_ortho, b200_general);
+      for (int lp = 0; lp < 20; lp++) {
+        if (b200_ortho[lp] > 0)
+          grid_library_counter_add(lp, GRID_BACKEND_B200, %s_ORTHO, b200_ortho[lp]);
+        if (b200_general[lp] > 0)
+          grid_library_counter_add(lp, GRID_BACKEND_B200, %s_GENERAL, b200_general[lp]);
+      }
+    }
+"""
 COLLOCATE_ARM = """
   case GRID_BACKEND_B200:
     grid_b200_collocate_task_list(task_list->b200, func, nlevels,
                                   (const grid_b200_buffer *)pab_blocks,
                                   (grid_b200_buffer **)grids);
-    break;
+""" + COUNTERS % ("GRID_COLLOCATE", "GRID_COLLOCATE") + """    break;
 """
 INTEGRATE_ARM = """
   case GRID_BACKEND_B200:
@@ -46,7 +58,7 @@ INTEGRATE_ARM = """
         (const grid_b200_buffer *)pab_blocks, (const grid_b200_buffer **)grids,
         (grid_b200_buffer *)hab_blocks, forces ? &forces[0][0] : NULL,
         virial ? &virial[0][0] : NULL);
-    break;
+""" + COUNTERS % ("GRID_INTEGRATE", "GRID_INTEGRATE") + """    break;
 """
 HEADER_LINES = """#include "grid_b200.h"
 #ifndef GRID_BACKEND_B200
@@ -76,7 +88,7 @@ def main(grid_dir: str, out_dir: str) -> None:
     src, at = insert_before(src, "\n  free(task_list->npts_local);", FREE_ARM, at)
     src, at = insert_before(src, "\n  default:", COLLOCATE_ARM, at)
     src, at = insert_before(src, "\n  default:", INTEGRATE_ARM, at)
-    if src.count("GRID_BACKEND_B200") != 3 or src.count("grid_b200_free_task_list") != 1:
+    if src.count("case GRID_BACKEND_B200") != 3 or src.count("grid_b200_free_task_list") != 1:
         raise SystemExit("patch_dispatcher: unexpected dispatcher layout")
     open(os.path.join(out_dir, "grid_task_list.c"), "w").write(src)
 
