@@ -466,15 +466,30 @@ def main():
                 rsgrid.halo_sum(t, sl, rank, world, dist)   # density: halos -> owners
                 rsgrid.halo_fill(t, sl, rank, world, dist)  # potential: owners -> halos
 
-    def step_resident():
-        tl.collocate(FUNC, pab, grids)
-        exchange(grids)
-        tl.integrate(TAU, pab if args.forces else None, grids, hab, forces, virial)
+    xt = {"armed": False, "grid_exchange": [], "hab_reduce": []}  # CUDA-event spans of the exchange pieces
+
+    def span(key, fn):
+        if not xt["armed"]:
+            fn()
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        xt[key].append((a, b))
+
+    def hab_sum():
         if slab_levels is not None:  # a block's tasks may live on several slabs
             if hab_exchange is not None:
                 hab_exchange.reduce(hab.device[: wl.pab_len], dist)
             else:
                 dist.all_reduce(hab.device)
+
+    def step_resident():
+        tl.collocate(FUNC, pab, grids)
+        span("grid_exchange", lambda: exchange(grids))
+        tl.integrate(TAU, pab if args.forces else None, grids, hab, forces, virial)
+        span("hab_reduce", hab_sum)
 
     def barrier():
         if world > 1:
@@ -508,11 +523,14 @@ def main():
     # ---- per-kernel roofline (device events inside the library) ---------------
     lib.set_timing(True)
     lib.timings()
+    xt["armed"] = world > 1
     for _ in range(args.steps):
         step_resident()
     barrier()
+    xt["armed"] = False
     tm = lib.timings()
     lib.set_timing(False)
+    exchange_ms = {k: sum(a.elapsed_time(b) for a, b in xt[k]) / args.steps for k in ("grid_exchange", "hab_reduce")}
     peaks = load_peaks()
     coll_ms = tm["collocate"][0] / args.steps
     int_ms = tm["integrate"][0] / args.steps
@@ -620,8 +638,9 @@ def main():
         own_hab, own_ref_slice = hab.device[: wl.pab_len], idx
         if slab_levels is not None:
             if hab_exchange is not None:
-                own_hab = hab_exchange.reduce(hab.device[: wl.pab_len], dist)
-                own_ref_slice = slice(hab_exchange.owned_start, hab_exchange.owned_start + hab_exchange.owned_len)
+                own_hab = hab_exchange.reduce(hab.device[: wl.pab_len], dist)[
+                    torch.from_numpy(hab_exchange.owned_local_index).to("cuda")]
+                own_ref_slice = hab_exchange.owned_global_index
             else:
                 dist.all_reduce(hab.device)
         torch.cuda.synchronize()
@@ -706,6 +725,7 @@ def main():
             # what the step spends outside this rank's kernels (rank 0's view): the grid exchange
             # (all-reduce, or halo sum + fill) and the owner reduction of H
             "exchange_ms_per_step": (ms_per_step - sum(v[0] for v in tm.values()) / args.steps) if world > 1 else 0.0,
+            "exchange_pieces_ms": exchange_ms if world > 1 else None,
             "create_task_list": {"ms": create_ms, "device_bytes": int(table_bytes),
                                  "in_steps": create_ms / ms_per_step},
         }

@@ -73,14 +73,57 @@ def cube_halfwidth(wl: Workload, level: int) -> int:
     return int(1 - lb)
 
 
-def make_slab_levels(wl: Workload, world: int) -> List[SlabLevel]:
+def _centre_planes(wl: Workload, ilev: int):
+    """Tasks of a level and the global z-plane of their cube centres."""
+    t = wl.tasks
+    lay = wl.layouts[ilev]
+    sel = np.nonzero(t["level_list"] == ilev + 1)[0]
+    ia = t["iatom_list"][sel] - 1
+    ja = t["jatom_list"][sel] - 1
+    zeta = _exponents(wl, wl.atom_kinds[ia] - 1, t["iset_list"][sel] - 1, t["ipgf_list"][sel] - 1)
+    zetb = _exponents(wl, wl.atom_kinds[ja] - 1, t["jset_list"][sel] - 1, t["jpgf_list"][sel] - 1)
+    rp_z = wl.atom_positions[ia, 2] + zetb / (zeta + zetb) * t["rab_list"][sel, 2]
+    nz = int(lay.npts_global[2])
+    return sel, np.floor(lay.dh_inv[2][2] * rp_z).astype(np.int64) % nz
+
+
+def balanced_limits(cost_per_plane: np.ndarray, world: int) -> List[Tuple[int, int]]:
+    """Contiguous plane ranges of (nearly) equal summed cost, at least one plane each.  The
+    reference cuts a level into slabs of equal thickness (get_limit) and then moves tasks
+    between neighbours to balance the load (distribute_tasks / load_balance_distributed,
+    src/task_list_methods.F:1889-2057); with one rank per GPU on a node it is simpler to cut
+    where the work is: a slab's tasks are the ones whose cube centre it owns."""
+    nz = cost_per_plane.size
+    cum = np.concatenate([[0.0], np.cumsum(cost_per_plane)])
+    cuts = [0]
+    for r in range(1, world):
+        target = cum[-1] * r / world
+        c = int(np.searchsorted(cum, target, side="left"))
+        if c > 0 and abs(cum[c - 1] - target) <= abs(cum[min(c, nz)] - target):
+            c -= 1
+        c = min(max(c, cuts[-1] + 1), nz - (world - r))
+        cuts.append(c)
+    cuts.append(nz)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def make_slab_levels(wl: Workload, world: int, balance: bool = True) -> List[SlabLevel]:
     levels = []
     for ilev, lay in enumerate(wl.layouts):
         npts = np.asarray(lay.npts_global, dtype=np.int64)
+        nz = int(npts[2])
         border = cube_halfwidth(wl, ilev) + 1
-        owned = [get_limit(int(npts[2]), world, r) for r in range(world)]
+        owned = [get_limit(nz, world, r) for r in range(world)]
+        if balance and wl.orthorhombic and world > 1 and nz >= world:
+            sel, centre = _centre_planes(wl, ilev)
+            if sel.size:
+                h = float(lay.dh[0][0])
+                cost = np.bincount(centre, weights=(wl.tasks["radius_list"][sel] / h) ** 3, minlength=nz)
+                cand = balanced_limits(cost, world)
+                if max(hi - lo for lo, hi in cand) + 2 * border <= nz:
+                    owned = cand
         thickest = max(hi - lo for lo, hi in owned)
-        distributed = wl.orthorhombic and world > 1 and thickest + 2 * border <= int(npts[2])
+        distributed = wl.orthorhombic and world > 1 and thickest + 2 * border <= nz
         levels.append(SlabLevel(distributed, npts, border, owned))
     return levels
 
@@ -93,27 +136,53 @@ def _exponents(wl: Workload, kinds, isets, ipgfs) -> np.ndarray:
     return out
 
 
+def block_home(wl: Workload, levels: Sequence[SlabLevel], world: int, owner_dist: np.ndarray) -> np.ndarray:
+    """Home rank of every matrix block (atom pair): the slab that works on most of the block's
+    tasks of the distributed levels (all of them, unless the pair sits at a slab boundary);
+    blocks without such tasks are dealt round-robin.  The block's tasks on the REPLICATED
+    levels run at home too and the block's H is owned there, so that only the blocks straddling
+    a slab boundary take part in the owner reduction of H (rs_gather_matrices' all-to-all,
+    src/task_list_methods.F:2419-2667, moves every block because DBCSR's matrix distribution is
+    unrelated to the rs_grid's; here the harness chooses the matrix distribution)."""
+    t = wl.tasks
+    b = t["block_num_list"] - 1
+    votes = np.zeros((wl.nblocks, world), dtype=np.int64)
+    on_dist = owner_dist >= 0
+    np.add.at(votes, (b[on_dist], owner_dist[on_dist]), 1)
+    home = np.argmax(votes, axis=1).astype(np.int32)
+    none = votes.sum(axis=1) == 0
+    home[none] = (np.nonzero(none)[0] % world).astype(np.int32)
+    return home
+
+
 def task_owner(wl: Workload, levels: Sequence[SlabLevel], world: int) -> np.ndarray:
     """Rank that works on every task.  Distributed levels: the rank owning the z-plane of
     the task's cube centre (the halo is wide enough for the whole cube).  Replicated
-    levels: tasks are dealt to ranks by matrix block (every rank holds the full grid)."""
+    levels (every rank holds the full grid): tasks follow their matrix block to its home
+    rank (`block_home`)."""
     t = wl.tasks
-    owner = np.zeros(wl.ntasks, dtype=np.int32)
+    owner = np.full(wl.ntasks, -1, dtype=np.int32)
     for ilev, (lay, sl) in enumerate(zip(wl.layouts, levels)):
         sel = np.nonzero(t["level_list"] == ilev + 1)[0]
         if sl.distributed:
-            ia = t["iatom_list"][sel] - 1
-            ja = t["jatom_list"][sel] - 1
-            zeta = _exponents(wl, wl.atom_kinds[ia] - 1, t["iset_list"][sel] - 1, t["ipgf_list"][sel] - 1)
-            zetb = _exponents(wl, wl.atom_kinds[ja] - 1, t["jset_list"][sel] - 1, t["jpgf_list"][sel] - 1)
-            rp_z = wl.atom_positions[ia, 2] + zetb / (zeta + zetb) * t["rab_list"][sel, 2]
-            nz = int(sl.npts_global[2])
-            centre = np.floor(lay.dh_inv[2][2] * rp_z).astype(np.int64) % nz
+            sel, centre = _centre_planes(wl, ilev)
             bounds = np.array([hi for _, hi in sl.owned])
             owner[sel] = np.searchsorted(bounds, centre, side="right")
-        else:
-            owner[sel] = (t["block_num_list"][sel] - 1) % world
+    home = block_home(wl, levels, world, owner)
+    rest = owner < 0
+    owner[rest] = home[t["block_num_list"][rest] - 1]
     return owner
+
+
+def block_owner(wl: Workload, levels: Sequence[SlabLevel], world: int) -> np.ndarray:
+    """Rank owning the H (and P) block of every atom pair in the slab decomposition."""
+    t = wl.tasks
+    owner = np.full(wl.ntasks, -1, dtype=np.int32)
+    for ilev, (lay, sl) in enumerate(zip(wl.layouts, levels)):
+        if sl.distributed:
+            sel = t["level_list"] == ilev + 1
+            owner[sel] = task_owner(wl, levels, world)[sel]
+    return block_home(wl, levels, world, owner)
 
 
 def local_workload(wl: Workload, levels: Sequence[SlabLevel], rank: int, world: int,
@@ -139,57 +208,76 @@ def local_workload(wl: Workload, levels: Sequence[SlabLevel], rank: int, world: 
 
 
 class HabExchange:
-    """Sums the ranks' partial H blocks into the blocks' owners -- the restatement of
+    """Sums the ranks' partial H blocks into the blocks' owners -- the counterpart of
     rs_gather_matrices / rs_scatter_matrices' all-to-all (src/task_list_methods.F:2419-2667)
     for ranks whose buffers hold only the blocks they touch (`compact_blocks=True`).
 
-    Matrix blocks are owned in contiguous ranges of (almost) equal size in doubles;
-    a rank's compacted buffer lists its blocks in ascending order, i.e. already grouped
-    by owner, so it IS the send buffer of one `all_to_all_single`; the receiver adds
-    every incoming segment into its owned slice through a precomputed index.  All
-    index arithmetic happens once, here."""
+    A block is owned by its home rank (`block_home`: the slab that computes most of it), so a
+    rank's compacted H buffer already holds the owned blocks in place; only the blocks it
+    touched but does not own travel: their elements are gathered (one index), exchanged with
+    one `all_to_all_single` and added into the owners' buffers through a precomputed index.
+    All index arithmetic happens once, here."""
 
     def __init__(self, wl: Workload, levels: Sequence[SlabLevel], rank: int, world: int):
         sizes = np.diff(np.append(wl.block_offsets.astype(np.int64), wl.pab_len))
         offsets = wl.block_offsets.astype(np.int64)
-        # contiguous ownership ranges balanced by size
-        bounds = np.searchsorted(np.cumsum(sizes), wl.pab_len * (np.arange(1, world) / world), side="left")
-        self.block_range = [(int(a), int(b)) for a, b in
-                            zip(np.concatenate([[0], bounds]), np.concatenate([bounds, [wl.nblocks]]))]
-        b_owner = np.zeros(wl.nblocks, dtype=np.int32)
-        for r, (a, b) in enumerate(self.block_range):
-            b_owner[a:b] = r
         towner = task_owner(wl, levels, world)
+        b_owner = block_owner(wl, levels, world)
         used = [np.unique(wl.tasks["block_num_list"][towner == r] - 1) for r in range(world)]
-        lo, hi = self.block_range[rank]
-        self.owned_start = int(offsets[lo]) if lo < wl.nblocks else wl.pab_len
-        self.owned_len = int(sizes[lo:hi].sum())
-        self.in_split = [int(sizes[used[rank][b_owner[used[rank]] == o]].sum()) for o in range(world)]
-        self.out_split, idx = [], []
-        for src in range(world):
-            mine = used[src][b_owner[used[src]] == rank]
-            self.out_split.append(int(sizes[mine].sum()))
-            if mine.size:
-                idx.append(np.repeat(offsets[mine] - self.owned_start - np.concatenate(
-                    [[0], np.cumsum(sizes[mine])[:-1]]), sizes[mine]) + np.arange(int(sizes[mine].sum())))
-        self.recv_index = np.concatenate(idx).astype(np.int64) if idx else np.zeros(0, np.int64)
+
+        def local_offsets(r):  # where rank r's compacted buffer keeps its blocks
+            off = np.full(wl.nblocks, -1, dtype=np.int64)
+            off[used[r]] = np.concatenate([[0], np.cumsum(sizes[used[r]])[:-1]]) if used[r].size else 0
+            return off
+
+        def elements(off, blocks):  # element indices of `blocks` (ascending) in a compacted buffer
+            if blocks.size == 0:
+                return np.zeros(0, np.int64)
+            return np.repeat(off[blocks] - np.concatenate([[0], np.cumsum(sizes[blocks])[:-1]]), sizes[blocks]) \
+                + np.arange(int(sizes[blocks].sum()))
+
+        mine = local_offsets(rank)
+        self.local_len = int(sizes[used[rank]].sum())
+        # what I send: my blocks owned elsewhere, grouped by owner (ascending block inside a group)
+        send_blocks = [used[rank][b_owner[used[rank]] == o] if o != rank else np.zeros(0, np.int64) for o in range(world)]
+        self.in_split = [int(sizes[bl].sum()) for bl in send_blocks]
+        self.send_index = np.concatenate([elements(mine, bl) for bl in send_blocks]).astype(np.int64)
+        # what I receive: from every other rank, the blocks it touched that I own
+        recv_blocks = [used[src][b_owner[used[src]] == rank] if src != rank else np.zeros(0, np.int64)
+                       for src in range(world)]
+        self.out_split = [int(sizes[bl].sum()) for bl in recv_blocks]
+        for bl in recv_blocks:  # an owner works on its own blocks (it is their majority slab)
+            assert np.all(mine[bl] >= 0), "an owned block is missing from the owner's buffer"
+        self.recv_index = np.concatenate([elements(mine, bl) for bl in recv_blocks]).astype(np.int64)
+        # the blocks I own: where they sit in my buffer and in the global block buffer
+        owned = used[rank][b_owner[used[rank]] == rank]
+        self.owned_local_index = elements(mine, owned)
+        self.owned_global_index = elements(offsets, owned)
+        self.owned_len = int(sizes[owned].sum())
         self._dev = {}
 
+    def _idx(self, name, device):
+        key = (name, str(device))
+        if key not in self._dev:
+            import torch
+
+            self._dev[key] = torch.from_numpy(getattr(self, name)).to(device)
+        return self._dev[key]
+
     def reduce(self, my_hab, dist):
-        """`my_hab`: the rank's compacted H buffer (torch tensor).  Returns the summed H
-        of the blocks this rank owns, as a tensor of `owned_len` doubles (the slice
-        [owned_start, owned_start + owned_len) of the global block buffer)."""
+        """`my_hab`: the rank's compacted H buffer (torch tensor), updated IN PLACE: afterwards
+        the blocks this rank owns hold the sum over all ranks (elements `owned_local_index`,
+        which are the elements `owned_global_index` of the global block buffer).  Returns it."""
         import torch
 
-        assert my_hab.numel() == sum(self.in_split)
+        assert my_hab.numel() == self.local_len
+        send = my_hab.index_select(0, self._idx("send_index", my_hab.device)) if self.send_index.size else \
+            torch.empty(0, dtype=my_hab.dtype, device=my_hab.device)
         recv = torch.empty(sum(self.out_split), dtype=my_hab.dtype, device=my_hab.device)
-        dist.all_to_all_single(recv, my_hab.contiguous(), self.out_split, self.in_split)
-        key = str(my_hab.device)
-        if key not in self._dev:
-            self._dev[key] = torch.from_numpy(self.recv_index).to(my_hab.device)
-        out = torch.zeros(self.owned_len, dtype=my_hab.dtype, device=my_hab.device)
-        out.index_add_(0, self._dev[key], recv)
-        return out
+        dist.all_to_all_single(recv, send, self.out_split, self.in_split)
+        if self.recv_index.size:
+            my_hab.index_add_(0, self._idx("recv_index", my_hab.device), recv)
+        return my_hab
 
 
 # ----------------------------------------------------------------------------

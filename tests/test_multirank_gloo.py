@@ -71,7 +71,7 @@ def _worker(rank, world, port, mode, result_file):
         levels = rsgrid.make_slab_levels(wl, world)
         assert any(l.distributed for l in levels)
         if world > 2:  # the case this test is for: halo wider than a slab
-            assert any(l.distributed and l.border > l.owned[0][1] - l.owned[0][0] for l in levels)
+            assert any(l.distributed and l.border > min(hi - lo for lo, hi in l.owned) for l in levels)
         mine = rsgrid.local_workload(wl, levels, rank, world)
         counts = torch.tensor([mine.ntasks], dtype=torch.int64)
         dist.all_reduce(counts)
@@ -111,13 +111,15 @@ def _worker(rank, world, port, mode, result_file):
         tl.integrate(False, None, grids, chab)
         tl.free()
         ex = rsgrid.HabExchange(wl, levels, rank, world)
-        assert np.array_equal(block_index_map(cmine).size, sum(ex.in_split))
-        own = ex.reduce(torch.from_numpy(chab.host), dist).numpy()
-        want = hab_full.host[ex.owned_start: ex.owned_start + ex.owned_len]
+        assert block_index_map(cmine).size == ex.local_len
+        own = ex.reduce(torch.from_numpy(chab.host), dist).numpy()[ex.owned_local_index]
+        want = hab_full.host[ex.owned_global_index]
         errs["hab"] = max(errs["hab"], float(np.abs(own - want).max()) if own.size else 0.0)
         covered = torch.tensor([ex.owned_len], dtype=torch.int64)
         dist.all_reduce(covered)
-        assert int(covered) == wl.pab_len  # the owned slices tile the whole block buffer
+        touched = np.unique(wl.tasks["block_num_list"] - 1)
+        sizes = np.diff(np.append(wl.block_offsets.astype(np.int64), wl.pab_len))
+        assert int(covered) == int(sizes[touched].sum())  # every block some task touches has one owner
     if rank == 0:
         np.save(result_file, np.array([errs["grid"], errs["hab"]]))
     dist.barrier()
