@@ -3,7 +3,7 @@
 # library's NCCL halo exchange; both verify their result against a one-GPU run (untimed)
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
-for mode in "--decomp slab --slab-compact"; do
+for mode in "--decomp slab --slab-compact" "--decomp blocks"; do
   tag=$(echo $mode | tr -d ' -')
   timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29721 \
      bench.py --gpus 8 --steps 20 --warmup 3 $mode 2>gpurun_out/bench8_$tag.err > gpurun_out/bench_h2o256_8gpu_${tag}_r02.json
