@@ -484,13 +484,19 @@ template <bool COLLOCATE, int LPHI> struct CtSlot {
   static constexpr int BYTES = COEF + (COLLOCATE ? NCP : 8 * NCP) * 8;
 };
 
+#ifndef B200_CT_CTAS
+#define B200_CT_CTAS 2   // CTAs per SM of the lp <= 2 class (1: 216 registers per consumer, deeper ring)
+#endif
+#ifndef B200_CT_NS
+#define B200_CT_NS 32    // ring depth of the lp <= 2 class
+#endif
 constexpr int kCtChunk = 16;   // visit records per staging chunk (one bulk copy)
 constexpr int kCtChunks = 4;   // staging ring depth
 
 template <bool COLLOCATE, int LPHI> struct CtConf {
   using Slot = CtSlot<COLLOCATE, LPHI>;
   // ring depth: as many slots as fit comfortably beside a second CTA (low classes)
-  static constexpr int NS = (Slot::BYTES <= 3072) ? 32 : ((Slot::BYTES <= 6144) ? 16 : ((Slot::BYTES <= 12288) ? 8 : 4));
+  static constexpr int NS = (Slot::BYTES <= 3072) ? B200_CT_NS : ((Slot::BYTES <= 6144) ? 16 : ((Slot::BYTES <= 12288) ? 8 : 4));
   static constexpr int BAR = 0;                       // u64 full[NS], empty[NS], cfull[4], cempty[4]
   static constexpr int ITEM = 16 * NS + 16 * kCtChunks;  // int: the CTA's current work item
   static constexpr int E2T = ITEM + 16;               // double[64]: 2^(j/64)
