@@ -678,7 +678,9 @@ def main():
         tl1.free()
         del grids1, hab1, pab1
         torch.cuda.empty_cache()
-        assert parity["grid_max_rel"] < 1e-10 and parity["hab_max_rel"] < 1e-10, f"multi-GPU parity failed: {parity}"
+        parity["ok"] = bool(parity["grid_max_rel"] < 1e-10 and parity["hab_max_rel"] < 1e-10)
+        if not parity["ok"] and rank == 0:  # reported in the line (and loudly here): the timing of a wrong result is void
+            print(f"bench.py: MULTI-GPU PARITY FAILED: {parity}", file=sys.stderr)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

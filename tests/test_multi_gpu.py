@@ -29,4 +29,4 @@ def test_two_ranks_match_one_gpu(b200, extra):
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     par = line["multi_gpu_parity"]
-    assert par is not None and par["grid_max_rel"] < 1e-10 and par["hab_max_rel"] < 1e-10, par
+    assert par is not None and par["ok"] and par["grid_max_rel"] < 1e-10 and par["hab_max_rel"] < 1e-10, par
