@@ -221,7 +221,7 @@ template <int PASS> __global__ void visitgen_kernel(const VisitGenArgs A) {
 // ---------------------------------------------------------------------------
 // Host: per-level build (task selection is the tiled path's: same criteria).
 // ---------------------------------------------------------------------------
-inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L, const std::vector<TaskDev> &tasks,
+inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L, const TaskVec &tasks,
                               const int first, const int last, std::vector<int> &generic_ids, const int item_cap,
                               cudaStream_t s) {
   cl.release();

@@ -12,6 +12,9 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <memory>
+#include <utility>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 
@@ -101,6 +104,22 @@ struct TaskDev {
   int use_ortho;               // orthorhombic && border_mask == 0
   int skip;                    // 2*radius < max|dh|  (collint.h:929-937)
 };
+
+// Host copy of the task records: a vector that does NOT zero its elements on resize (the
+// builder fills 10^6 - 10^7 records of 360 bytes in parallel; a value-initialising resize
+// would first touch and zero all of them on one thread).
+template <class T> struct DefaultInitAlloc : std::allocator<T> {
+  template <class U> struct rebind {
+    using other = DefaultInitAlloc<U>;
+  };
+  template <class U, class... A> void construct(U *p, A &&...a) {
+    if constexpr (sizeof...(A) == 0)
+      ::new ((void *)p) U;
+    else
+      ::new ((void *)p) U(std::forward<A>(a)...);
+  }
+};
+using TaskVec = std::vector<TaskDev, DefaultInitAlloc<TaskDev>>;
 
 // (lx,ly,lz) of coset index c, for c < ncoset(kMaxLp) -- filled at load time.
 struct OrbTable {

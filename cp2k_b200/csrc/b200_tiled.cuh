@@ -59,6 +59,9 @@ namespace b200 {
 #ifndef B200_CTAS_HI
 #define B200_CTAS_HI 3
 #endif
+#ifndef B200_LPHI_LO
+#define B200_LPHI_LO 2   // kernels whose largest lp is <= this get B200_CTAS_LO CTAs per SM
+#endif
 constexpr int kBX = 8, kBY = 8, kBZ = B200_KBZ;  // block (warp footprint)
 constexpr int kTiledThreads = 128;            // 4 autonomous warps
 constexpr int kTiledWarps = kTiledThreads / 32;
@@ -361,7 +364,7 @@ struct CreateTimer {
   }
 };
 
-inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vector<TaskDev> &tasks,
+inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &tasks,
                               const TaskDev *d_tasks, const int first, const int last,
                               std::vector<int> &generic_ids, cudaStream_t s) {
   CreateTimer tm(s);
@@ -372,37 +375,59 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const std::vect
             nbz = (L.npts_local[2] + kBZ - 1) / kBZ;
   const size_t nblocks = (size_t)nbx * nby * nbz;
 
+  // Select the tasks of the tiled path (two parallel passes over the level's records:
+  // classify, then compact in task order -- the result does not depend on the thread count).
   std::vector<TTask> tt;
   int max_n = 0, max_lp0 = 0, max_nb = 0;
-  for (int it = first; it < last; it++) {
-    const TaskDev &T = tasks[it];
-    bool ok = T.use_ortho && !T.skip;
-    int n = 0;
-    if (ok) {
-      n = (int)llround(T.disr_radius / drmin);
-      // the discretised radius must be exactly n*drmin for the tables to apply
-      ok = (n >= 1 && n <= kTiledMaxN && T.disr_radius == drmin * fmax(1.0, (double)n));
-      ok = ok && (T.la_max + T.lb_max <= kTiledMaxLp);
-      for (int d = 0; d < 3; d++)
-        ok = ok && (-T.lb_cube[d] <= kTiledMaxNb);
+  {
+    const int nt = last - first;
+    std::vector<int> nidx(std::max(nt, 1));  // radius index, 0 = generic path
+#pragma omp parallel for schedule(static) reduction(max : max_n, max_lp0, max_nb)
+    for (int k = 0; k < nt; k++) {
+      const TaskDev &T = tasks[first + k];
+      bool ok = T.use_ortho && !T.skip;
+      int n = 0;
+      if (ok) {
+        n = (int)llround(T.disr_radius / drmin);
+        // the discretised radius must be exactly n*drmin for the tables to apply
+        ok = (n >= 1 && n <= kTiledMaxN && T.disr_radius == drmin * fmax(1.0, (double)n));
+        ok = ok && (T.la_max + T.lb_max <= kTiledMaxLp);
+        for (int d = 0; d < 3; d++)
+          ok = ok && (-T.lb_cube[d] <= kTiledMaxNb);
+      }
+      nidx[k] = ok ? n : 0;
+      if (ok) {
+        max_n = std::max(max_n, n), max_lp0 = std::max(max_lp0, T.la_max + T.lb_max);
+        for (int d = 0; d < 3; d++)
+          max_nb = std::max(max_nb, -T.lb_cube[d]);
+      }
     }
-    if (!ok) {
-      generic_ids.push_back(it);
-      continue;
+    std::vector<int> pos(std::max(nt, 1));  // position of task k among the tiled (or the generic) ones
+    int n_tiled = 0, n_generic = 0;
+    for (int k = 0; k < nt; k++)
+      pos[k] = nidx[k] ? n_tiled++ : n_generic++;
+    tt.resize(n_tiled);
+    const size_t g0 = generic_ids.size();
+    generic_ids.resize(g0 + n_generic);
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < nt; k++) {
+      const int it = first + k;
+      if (nidx[k] == 0) {
+        generic_ids[g0 + pos[k]] = it;
+        continue;
+      }
+      const TaskDev &T = tasks[it];
+      TTask X;
+      for (int d = 0; d < 3; d++) {
+        X.roff[d] = T.roffset[d];
+        X.cc[d] = T.cubecenter[d] - L.shift_local[d];
+        X.nb[d] = -T.lb_cube[d];
+      }
+      X.n = nidx[k], X.lp0 = T.la_max + T.lb_max, X.task = it;
+      X.zl2 = T.zetp * 1.4426950408889634074;
+      X.pad[0] = X.pad[1] = X.pad[2] = 0;
+      tt[pos[k]] = X;
     }
-    TTask X;
-    for (int d = 0; d < 3; d++) {
-      X.roff[d] = T.roffset[d];
-      X.cc[d] = T.cubecenter[d] - L.shift_local[d];
-      X.nb[d] = -T.lb_cube[d];
-      max_nb = std::max(max_nb, X.nb[d]);
-    }
-    X.n = n, X.lp0 = T.la_max + T.lb_max, X.task = it;
-    X.zl2 = T.zetp * 1.4426950408889634074;
-    X.pad[0] = X.pad[1] = X.pad[2] = 0;
-    tt.push_back(X);
-    max_n = std::max(max_n, n);
-    max_lp0 = std::max(max_lp0, X.lp0);
   }
   tl.ntasks_tiled = (int)tt.size();
   tl.max_lp0 = max_lp0;
@@ -957,7 +982,7 @@ __device__ __forceinline__ void run_pairs(const LaneCtx &c, const int first, con
 }
 
 template <bool COLLOCATE, int LPLO, int LPHI, int SUB = 0>
-__global__ void __launch_bounds__(kTiledThreads, (LPHI <= 2) ? B200_CTAS_LO : B200_CTAS_HI) tiled_kernel(const TiledArgs A) {
+__global__ void __launch_bounds__(kTiledThreads, (LPHI <= B200_LPHI_LO) ? B200_CTAS_LO : B200_CTAS_HI) tiled_kernel(const TiledArgs A) {
   double *const smem = tiled_smem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int STAGE = stage_doubles(LPHI);
@@ -1229,7 +1254,7 @@ __global__ void stats_kernel(const StatsArgs A) {
 }
 
 inline void compute_stats(const TaskDev *d_tasks, const int ntasks, const std::vector<LevelDev> &levels,
-                          const std::vector<TaskDev> &h_tasks, double *stats, cudaStream_t s) {
+                          const TaskVec &h_tasks, double *stats, cudaStream_t s) {
   (void)h_tasks;
   LevelDev *d_levels = nullptr;
   double *d_out = nullptr;

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <omp.h>
 #include <parallel/algorithm>
 #include <vector>
 
@@ -123,7 +124,7 @@ template <typename T> struct DevBuf {
     B200_CHECK(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
     cap = n;
   }
-  void upload(const std::vector<T> &v, cudaStream_t s) {
+  template <class Vec> void upload(const Vec &v, cudaStream_t s) {
     ensure(v.size());
     if (!v.empty()) {
       B200_CHECK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
@@ -166,7 +167,7 @@ struct TaskList {
   int ntasks = 0, nlevels = 0, natoms = 0, nkinds = 0, nblocks = 0;
   std::vector<LevelDev> levels;
   std::vector<LevelInfo> linfo;
-  std::vector<TaskDev> h_tasks;
+  TaskVec h_tasks;
   DevBuf<TaskDev> d_tasks;
   DevBuf<double> d_sphi;
   DevBuf<int> d_iota, d_generic_ids, d_block_task_ids, d_block_first;
@@ -624,39 +625,82 @@ static void build_task_list(
   }
 
   tick("task records (host)");
-  // per-level ranges and maxima
+  // per-level ranges and maxima (threads reduce into private copies, merged at the end)
   for (int l = 0; l < nlevels; l++)
     tl.linfo[l].first = tl.linfo[l].last = 0;
-  for (int it = 0; it < ntasks; it++) {
-    const TaskDev &T = tl.h_tasks[it];
-    LevelInfo &li = tl.linfo[T.level];
-    if (li.last == li.first && (it == 0 || tl.h_tasks[it - 1].level != T.level))
-      li.first = it;
-    li.last = it + 1;
-    const int lp0 = T.la_max + T.lb_max;
-    li.max_lp0 = std::max(li.max_lp0, lp0);
-    if (!T.skip) {
-      for (int d = 0; d < 3; d++) {
-        const int w = T.use_ortho ? 2 - 2 * T.lb_cube[d] : T.index_max[d] - T.index_min[d] + 1;
-        li.max_w = std::max(li.max_w, w);
+  {
+    struct Acc {
+      std::vector<LevelInfo> li;
+      TaskList::SizeClass sc[kNumSizeClasses];
+      int max_nsgf_set = 1, max_ncoset_raw = 1, max_la = 0, max_lb = 0, max_block_size = 1;
+      bool combo[kMaxLSide + 1][kMaxLSide + 1] = {};
+    };
+    std::vector<Acc> accs;
+#pragma omp parallel
+    {
+#pragma omp single
+      accs.resize(omp_get_num_threads());
+      Acc &A = accs[omp_get_thread_num()];
+      A.li.assign(nlevels, LevelInfo());
+      for (auto &x : A.li)
+        x.first = INT_MAX, x.last = 0;
+#pragma omp for schedule(static)
+      for (int it = 0; it < ntasks; it++) {
+        const TaskDev &T = tl.h_tasks[it];
+        LevelInfo &li = A.li[T.level];
+        li.first = std::min(li.first, it);
+        li.last = std::max(li.last, it + 1);
+        const int lp0 = T.la_max + T.lb_max;
+        li.max_lp0 = std::max(li.max_lp0, lp0);
+        if (!T.skip)
+          for (int d = 0; d < 3; d++) {
+            const int w = T.use_ortho ? 2 - 2 * T.lb_cube[d] : T.index_max[d] - T.index_min[d] + 1;
+            li.max_w = std::max(li.max_w, w);
+          }
+        if (!T.use_ortho)
+          li.max_lp0_general = std::max(li.max_lp0_general, lp0);
+        A.max_nsgf_set = std::max({A.max_nsgf_set, T.nsgf_seta, T.nsgf_setb});
+        A.max_ncoset_raw = std::max({A.max_ncoset_raw, T.ncoseta, T.ncosetb});
+        TaskList::SizeClass &C = A.sc[size_class(T)];
+        C.max_nsgf_set = std::max({C.max_nsgf_set, T.nsgf_seta, T.nsgf_setb});
+        C.max_ncoset_raw = std::max({C.max_ncoset_raw, T.ncoseta, T.ncosetb});
+        C.max_la = std::max(C.max_la, T.la_max), C.max_lb = std::max(C.max_lb, T.lb_max);
+        A.max_la = std::max(A.max_la, T.la_max), A.max_lb = std::max(A.max_lb, T.lb_max);
+        B200_ASSERT(T.la_max <= kMaxLSide && T.lb_max <= kMaxLSide, "angular momentum beyond kMaxLSide");
+        A.combo[T.la_max][T.lb_max] = true;
+        A.max_block_size = std::max(A.max_block_size, T.nsgfa * T.nsgfb);
       }
     }
-    if (!T.use_ortho)
-      li.max_lp0_general = std::max(li.max_lp0_general, lp0);
-    tl.max_nsgf_set = std::max({tl.max_nsgf_set, T.nsgf_seta, T.nsgf_setb});
-    tl.max_ncoset_raw = std::max({tl.max_ncoset_raw, T.ncoseta, T.ncosetb});
-    {
-      TaskList::SizeClass &C = tl.sclass[size_class(T)];
-      C.max_nsgf_set = std::max({C.max_nsgf_set, T.nsgf_seta, T.nsgf_setb});
-      C.max_ncoset_raw = std::max({C.max_ncoset_raw, T.ncoseta, T.ncosetb});
-      C.max_la = std::max(C.max_la, T.la_max), C.max_lb = std::max(C.max_lb, T.lb_max);
+    bool combo[kMaxLSide + 1][kMaxLSide + 1] = {};
+    for (const Acc &A : accs) {
+      for (int l = 0; l < nlevels; l++) {
+        LevelInfo &li = tl.linfo[l];
+        const LevelInfo &x = A.li[l];
+        if (x.last > 0) {
+          li.first = (li.last == 0) ? x.first : std::min(li.first, x.first);
+          li.last = std::max(li.last, x.last);
+        }
+        li.max_lp0 = std::max(li.max_lp0, x.max_lp0), li.max_w = std::max(li.max_w, x.max_w);
+        li.max_lp0_general = std::max(li.max_lp0_general, x.max_lp0_general);
+      }
+      for (int k = 0; k < kNumSizeClasses; k++) {
+        TaskList::SizeClass &C = tl.sclass[k];
+        C.max_nsgf_set = std::max(C.max_nsgf_set, A.sc[k].max_nsgf_set);
+        C.max_ncoset_raw = std::max(C.max_ncoset_raw, A.sc[k].max_ncoset_raw);
+        C.max_la = std::max(C.max_la, A.sc[k].max_la), C.max_lb = std::max(C.max_lb, A.sc[k].max_lb);
+      }
+      tl.max_nsgf_set = std::max(tl.max_nsgf_set, A.max_nsgf_set);
+      tl.max_ncoset_raw = std::max(tl.max_ncoset_raw, A.max_ncoset_raw);
+      tl.max_la = std::max(tl.max_la, A.max_la), tl.max_lb = std::max(tl.max_lb, A.max_lb);
+      tl.max_block_size = std::max(tl.max_block_size, A.max_block_size);
+      for (int a = 0; a <= kMaxLSide; a++)
+        for (int b2 = 0; b2 <= kMaxLSide; b2++)
+          combo[a][b2] = combo[a][b2] || A.combo[a][b2];
     }
-    tl.max_la = std::max(tl.max_la, T.la_max);
-    if (std::find(tl.l_combos.begin(), tl.l_combos.end(), std::make_pair(T.la_max, T.lb_max)) ==
-        tl.l_combos.end())
-      tl.l_combos.push_back(std::make_pair(T.la_max, T.lb_max));
-    tl.max_lb = std::max(tl.max_lb, T.lb_max);
-    tl.max_block_size = std::max(tl.max_block_size, T.nsgfa * T.nsgfb);
+    for (int a = 0; a <= kMaxLSide; a++)
+      for (int b2 = 0; b2 <= kMaxLSide; b2++)
+        if (combo[a][b2])
+          tl.l_combos.push_back(std::make_pair(a, b2));
   }
   B200_ASSERT(tl.max_la + 3 <= kMaxLSide && tl.max_lb + 3 <= kMaxLSide,
               "angular momentum beyond what this build supports (kMaxLSide)");
@@ -671,20 +715,23 @@ static void build_task_list(
   std::iota(iota.begin(), iota.end(), 0);
   tl.d_iota.upload(iota, s);
 
-  // tasks grouped by matrix block for the hab/forces kernel
+  // tasks grouped by matrix block for the hab/forces kernel: sorted by a packed key
+  // (block, iset, jset) read from compact arrays, not from the 360-byte records
   std::vector<int> by_block(ntasks);
-  std::iota(by_block.begin(), by_block.end(), 0);
-  __gnu_parallel::stable_sort(by_block.begin(), by_block.end(), [&](int a, int b) {
-    const TaskDev &A = tl.h_tasks[a], &B = tl.h_tasks[b];
-    if (A.block_num != B.block_num)
-      return A.block_num < B.block_num;
-    if (A.iset != B.iset)
-      return A.iset < B.iset;
-    return A.jset < B.jset;
-  });
+  std::vector<unsigned long long> bkey(ntasks);
+  std::vector<unsigned char> tcls(ntasks);
+#pragma omp parallel for schedule(static)
+  for (int it = 0; it < ntasks; it++) {
+    const TaskDev &T = tl.h_tasks[it];
+    B200_ASSERT(T.iset < 1024 && T.jset < 1024, "more than 1024 sets per kind");
+    bkey[it] = ((unsigned long long)T.block_num << 20) | ((unsigned long long)T.iset << 10) | (unsigned long long)T.jset;
+    tcls[it] = (unsigned char)size_class(T);
+    by_block[it] = it;
+  }
+  __gnu_parallel::stable_sort(by_block.begin(), by_block.end(), [&](int a, int b) { return bkey[a] < bkey[b]; });
   std::vector<int> block_first(nblocks + 1, 0);
   for (int it = 0; it < ntasks; it++)
-    block_first[tl.h_tasks[by_block[it]].block_num + 1]++;
+    block_first[(size_t)(bkey[it] >> 20) + 1]++;
   for (int b = 0; b < nblocks; b++)
     block_first[b + 1] += block_first[b];
   tl.d_block_task_ids.upload(by_block, s);
@@ -709,14 +756,14 @@ static void build_task_list(
       for (int k = 0; k < kNumSizeClasses; k++) {
         ch.c0[k] = (int)chunked.size();
         for (int it = ch.t0; it < ch.t1; it++)
-          if (size_class(tl.h_tasks[by_block[it]]) == k)
+          if (tcls[by_block[it]] == k)
             chunked.push_back(by_block[it]);
         ch.c0[k + 1] = (int)chunked.size();
       }
     for (int k = 0; k < kNumSizeClasses; k++) {
       tl.g0[k] = (int)global.size();
       for (int it = 0; it < ntasks; it++)
-        if (size_class(tl.h_tasks[by_block[it]]) == k)
+        if (tcls[by_block[it]] == k)
           global.push_back(by_block[it]);
       tl.g0[k + 1] = (int)global.size();
     }
