@@ -278,7 +278,7 @@ def cpu_reference_timing(wl, steps, warmup, forces, budget_s=25.0, virial=False)
     per_task = t_probe / max(probe.ntasks, 1)
     full_est = per_task * wl.ntasks
     total_steps = steps + warmup
-    frac = min(1.0, budget_s / max(full_est * total_steps, 1e-9))
+    frac = min(1.0, max(budget_s, 1e-3) / max(full_est * total_steps, 1e-9))
     if frac >= 0.999:
         sample, desc = wl, f"full task list ({wl.ntasks} tasks)"
     else:
@@ -419,10 +419,20 @@ def main():
         wl = split_blocks(wl_full, world, rank)
     torch.cuda.synchronize()
     free0 = torch.cuda.mem_get_info()[0]
-    t_create = time.perf_counter()
-    tl = wl.create(lib)
-    torch.cuda.synchronize()
-    create_ms = (time.perf_counter() - t_create) * 1e3
+    # create is host-heavy (sorting, table building) and the box's host cores are noisy: three
+    # creates, the fastest is quoted, all are reported.  The first one of a process also pays CUDA
+    # module loading and the OpenMP pool start; CP2K calls create once per MD step, warm.
+    create_all_ms, tl = [], None
+    for _ in range(3):
+        if tl is not None:
+            tl.free()
+        torch.cuda.synchronize()
+        t_create = time.perf_counter()
+        tl = wl.create(lib)
+        torch.cuda.synchronize()
+        create_all_ms.append((time.perf_counter() - t_create) * 1e3)
+    create_ms = min(create_all_ms)
+    lib.release_cache()  # the builders' scratch, kept for the next create
     table_bytes = free0 - torch.cuda.mem_get_info()[0]  # device memory the task list holds
     st = lib.stats(tl)
     flops_local = st["flops_collocate"] + st["flops_integrate"]
@@ -728,7 +738,8 @@ def main():
             # (all-reduce, or halo sum + fill) and the owner reduction of H
             "exchange_ms_per_step": (ms_per_step - sum(v[0] for v in tm.values()) / args.steps) if world > 1 else 0.0,
             "exchange_pieces_ms": exchange_ms if world > 1 else None,
-            "create_task_list": {"ms": create_ms, "device_bytes": int(table_bytes),
+            "create_task_list": {"ms": create_ms, "all_ms": create_all_ms,
+                                 "device_bytes": int(table_bytes),
                                  "in_steps": create_ms / ms_per_step},
         }
         print(json.dumps(line))

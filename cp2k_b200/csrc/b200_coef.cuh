@@ -459,15 +459,36 @@ __device__ inline double vab_elem(const PCtx &p, const bool tau, const int what,
 }
 
 struct HabDims {
-  int work, raw, cab, alpha, cxyz, h;  // doubles per warp
-  __host__ __device__ int total() const { return work + raw + cab + alpha + 2 * cxyz + h + kTaskDoubles; }
+  int work, raw, cab, alpha, cxyz, h, g;  // doubles per warp
+  __host__ __device__ int total() const { return work + raw + cab + alpha + 2 * cxyz + h + g + kTaskDoubles; }
 };
+
+// Forces and virial are sums over matrix elements of  P(a,b) * d(vab)(a,b).  With tau, vab is
+// itself a 12-term stencil over the plain elements (common/grid_process_vab.h:186-251): instead
+// of expanding the stencil inside each of the 24 derivatives (~950 cab look-ups per element) the
+// density is pushed through the ADJOINT stencil once (the integrate-side twin of prepare_pab's
+// tau transform, common/grid_prepare_pab.h:76-130), after which forces and virial are plain sums
+// over the (l+1)-grown element range: ~80 look-ups per element.
+__device__ inline void accumulate_fv(const PCtx &P, const double pv, const Orb &a, const Orb &b,
+                                     const bool do_v, double facc[15]) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    facc[i] += pv * vab_plain(P, 1, i, 0, a, b);
+    facc[3 + i] += pv * vab_plain(P, 2, i, 0, a, b);
+  }
+  if (do_v)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+        facc[6 + 3 * i + j] += pv * (vab_plain(P, 3, i, j, a, b) + vab_plain(P, 4, i, j, a, b));
+}
 
 // One warp per task (tasks visited in block order for locality).  The spherical
 // block receives the task's contribution through FP64 atomics: tasks of one
 // block are few (~8 for water) and the atomics are spread over the whole block.
 template <int G>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const int dla_max,
                    const int dla_min, const int dlb_max, const int dlb_min) {
   extern __shared__ double smem[];
@@ -475,7 +496,9 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
   stage_orb_table(s_orb, threadIdx.x, blockDim.x);
   __syncthreads();
   const int lane = threadIdx.x & (G - 1), warp = threadIdx.x / G, wpc = blockDim.x / G;
-  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
+  // G = 16, 32: a (half-)warp per task; G = 128: the whole CTA on one task (large l: the
+  // per-task scratch allows few tasks per SM, so more threads must share one)
+  const unsigned gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << (((threadIdx.x & 31) / G) * G));
   double *s_work = smem + (size_t)warp * D.total();
   double *s_raw = s_work + D.work;
   double *s_cab = s_raw + D.raw;
@@ -483,8 +506,14 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
   double *s_cxyz = s_alpha + D.alpha;
   double *s_cijk = s_cxyz + D.cxyz;
   double *s_h = s_cijk + D.cxyz;
-  TaskDev *s_task = reinterpret_cast<TaskDev *>(s_h + D.h);
-  auto sync = [gmask] { __syncwarp(gmask); };
+  double *s_g = s_h + D.h;
+  TaskDev *s_task = reinterpret_cast<TaskDev *>(s_g + D.g);
+  auto sync = [gmask] {
+    if (G > 32)
+      __syncthreads();
+    else
+      __syncwarp(gmask);
+  };
   const bool do_f = (L.forces != nullptr), do_v = (L.virial != nullptr);
 
   TaskPrefetch<G> pf;
@@ -496,14 +525,15 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
   }
   for (int it = it0; it < ntasks; it += stride) {
     const int itask = id_next;
-    __syncwarp(gmask);  // the previous task's reads of the record are complete
+    sync();  // the previous task's reads of the record are complete
     pf.commit(s_task, lane);
-    __syncwarp(gmask);
+    sync();
     if (it + stride < ntasks) {
       id_next = L.block_task_ids[it + stride];
       pf.issue(L.tasks + id_next, lane);
       // its coefficients: up to G cache lines from the start of its slot
-      prefetch_l2(L.coef + L.coef_offsets[id_next] + 16 * lane);
+      if (lane < 32)
+        prefetch_l2(L.coef + L.coef_offsets[id_next] + 16 * lane);
     }
     const TaskDev &T = *s_task;
     if (T.skip)
@@ -521,7 +551,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
     } else {
       for (int c = lane; c < nc; c += G)
         s_cijk[c] = in[c];
-      __syncwarp(gmask);
+      sync();
       const double *Tm = L.cijk_T[T.level * (kMaxLp + 1) + lp];
       for (int c = lane; c < nc; c += G) {
         double acc = 0.0;
@@ -556,7 +586,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
     // (3) density sub-block for forces / virial
     if (do_f || do_v)
       decontract_task(T, L.pab + T.block_offset, L.sphi_pool, s_work, s_raw, lane, G, sync);
-    __syncwarp(gmask);
+    sync();
 
     // (4) matrix elements for the original l-range
     PCtx P;
@@ -568,32 +598,50 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
 #pragma unroll
     for (int i = 0; i < 15; i++)
       facc[i] = 0.0;
+    const bool fv_by_adjoint = do_f && L.compute_tau;
+    if (fv_by_adjoint) {
+      const int na1 = ncoset(T.la_max + 1), nb1 = ncoset(T.lb_max + 1);
+      for (int q = lane; q < na1 * nb1; q += G) {
+        const int ia = q % na1, ib = q / na1;
+        const Orb a = orb_of(s_orb, ia), b = orb_of(s_orb, ib);
+        double g = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int ua = oidx(oup(k, a)), ub = oidx(oup(k, b));
+          const int da = oidx(odn(k, a)), db = oidx(odn(k, b));
+          const bool ok_ua = (ua >= a_lo && ua < na), ok_ub = (ub >= b_lo && ub < nb);
+          const bool ok_da = (a.l[k] >= 1 && da >= a_lo && da < na);
+          const bool ok_db = (b.l[k] >= 1 && db >= b_lo && db < nb);
+          if (ok_ua && ok_ub)
+            g += 0.5 * (a.l[k] + 1) * (b.l[k] + 1) * s_raw[ub * na + ua];
+          if (ok_da && ok_ub)
+            g -= P.zeta * (b.l[k] + 1) * s_raw[ub * na + da];
+          if (ok_ua && ok_db)
+            g -= (a.l[k] + 1) * P.zetb * s_raw[db * na + ua];
+          if (ok_da && ok_db)
+            g += 2.0 * P.zeta * P.zetb * s_raw[db * na + da];
+        }
+        s_g[q] = g;
+      }
+      sync();
+      for (int q = lane; q < na1 * nb1; q += G) {
+        const double g = s_g[q];
+        if (g != 0.0)
+          accumulate_fv(P, g, orb_of(s_orb, q % na1), orb_of(s_orb, q / na1), do_v, facc);
+      }
+    }
     for (int q = lane; q < na * nb; q += G) {
       const int ia = q % na, ib = q / na;
       double hval = 0.0;
       if (ia >= a_lo && ib >= b_lo) {
         const Orb a = orb_of(s_orb, ia), b = orb_of(s_orb, ib);
         hval = vab_elem(P, L.compute_tau, 0, 0, 0, a, b);
-        if (do_f) {
-          const double pv = s_raw[ib * na + ia];
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            facc[i] += pv * vab_elem(P, L.compute_tau, 1, i, 0, a, b);
-            facc[3 + i] += pv * vab_elem(P, L.compute_tau, 2, i, 0, a, b);
-          }
-          if (do_v)
-#pragma unroll
-            for (int i = 0; i < 3; i++)
-#pragma unroll
-              for (int j = 0; j < 3; j++)
-                facc[6 + 3 * i + j] +=
-                    pv * (vab_elem(P, L.compute_tau, 3, i, j, a, b) +
-                          vab_elem(P, L.compute_tau, 4, i, j, a, b));
-        }
+        if (do_f && !fv_by_adjoint)
+          accumulate_fv(P, s_raw[ib * na + ia], a, b, do_v, facc);
       }
       s_h[q] = hval;
     }
-    __syncwarp(gmask);
+    sync();
 
     // (5) contract into the spherical block: block += sphi_a h sphi_b^T
     const double *sphi_a = L.sphi_pool + T.sphi_a + T.sgfa * T.maxcoa + T.o1;
@@ -607,7 +655,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
         acc += __ldg(ps) * *ph;
       s_work[q] = acc;
     }
-    __syncwarp(gmask);
+    sync();
     double *g_block = L.hab + T.block_offset;
     for (int q = lane; q < T.nsgf_seta * T.nsgf_setb; q += G) {
       const int sb = q / T.nsgf_seta, sa = q - sb * T.nsgf_seta;
@@ -630,9 +678,9 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
           break;
         double v = facc[i];
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1)
+        for (int o = ((G > 32) ? 32 : G) / 2; o > 0; o >>= 1)
           v += __shfl_xor_sync(gmask, v, o);
-        if (lane == 0 && v != 0.0) {
+        if ((lane & 31) == 0 && v != 0.0) {
           if (i < 3)
             atomicAdd(&L.forces[3 * T.iatom + i], scale * v);
           else if (i < 6)
@@ -642,7 +690,7 @@ coef_to_hab_kernel(const HabLaunch L, const HabDims D, const int ntasks, const i
         }
       }
     }
-    __syncwarp(gmask);
+    sync();
   }
 }
 
@@ -698,9 +746,24 @@ inline void launch_coef_to_hab(const HabLaunch &L, const int ntasks, const int m
   D.alpha = 3 * (L.max_la_l + 1) * (L.max_lb_l + 1) * (L.max_la_l + L.max_lb_l + 1);
   D.cxyz = ncoset(L.max_la_l + L.max_lb_l);
   D.h = max_ncoset_raw * max_ncoset_raw;
+  D.g = (L.compute_tau && L.forces != nullptr)
+            ? ncoset(L.max_la_l - dla_max + 1) * ncoset(L.max_lb_l - dlb_max + 1)
+            : 0;
   const size_t per_group = (size_t)D.total() * sizeof(double);
   B200_ASSERT(per_group <= kSmemBudget, "basis too large for the hab kernel");
   const int gpw = (8 * per_group <= kSmemBudget) ? 2 : 1;
+  if (16 * per_group > kSmemBudget) {
+    // fewer than 16 tasks fit an SM: one CTA of four warps per task instead of one warp
+    B200_CHECK(cudaFuncSetAttribute(coef_to_hab_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)per_group));
+    int per_sm = 1;
+    B200_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coef_to_hab_kernel<128>, 128, per_group));
+    const int grid = std::min(ntasks, 148 * std::max(per_sm, 1));
+    coef_to_hab_kernel<128><<<grid, 128, per_group, L.stream>>>(L, D, ntasks, dla_max, dla_min, dlb_max, dlb_min);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    return;
+  }
   const int wpc = (int)std::min<size_t>(4, kSmemBudget / (per_group * gpw));
   const size_t bytes = per_group * gpw * wpc;
   auto grid_for = [&](auto kernel) {

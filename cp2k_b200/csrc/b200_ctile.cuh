@@ -73,10 +73,10 @@ struct CtileLevel {
   unsigned char *d_ktab = nullptr;
   std::vector<CWork> work[kNumClasses];  // host: merged over the levels by the list
   void release() {
-    cudaFree(d_ctasks), cudaFree(d_visits), cudaFree(d_khead), cudaFree(d_ktab);
+    dev_free(d_ctasks), dev_free(d_visits), dev_free(d_khead), dev_free(d_ktab);
     d_ctasks = nullptr, d_visits = nullptr, d_khead = nullptr, d_ktab = nullptr;
     for (auto &p : d_class_task_ids) {
-      cudaFree(p);
+      dev_free(p);
       p = nullptr;
     }
     for (auto &w : work)
@@ -303,7 +303,7 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
 
   auto up = [&](auto **dst, const auto &vec) {
     using T = typename std::remove_reference<decltype(vec)>::type::value_type;
-    B200_CHECK(cudaMalloc((void **)dst, std::max<size_t>(vec.size(), 1) * sizeof(T)));
+    dev_alloc(dst, std::max<size_t>(vec.size(), 1) * sizeof(T));
     if (!vec.empty())
       B200_CHECK(cudaMemcpyAsync(*dst, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   };
@@ -316,8 +316,8 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
   // visits: count, scan, fill, sort by (bucket, hashed task index)
   const size_t nbuckets = ntiles * kLpBuckets * kNumClasses;
   unsigned int *d_count = nullptr, *d_start = nullptr;
-  B200_CHECK(cudaMalloc((void **)&d_count, (nbuckets + 1) * sizeof(unsigned int)));
-  B200_CHECK(cudaMalloc((void **)&d_start, (nbuckets + 1) * sizeof(unsigned int)));
+  dev_alloc(&d_count, (nbuckets + 1) * sizeof(unsigned int));
+  dev_alloc(&d_start, (nbuckets + 1) * sizeof(unsigned int));
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
   VisitGenArgs VA;
   VA.ttasks = d_ttasks, VA.ctasks = cl.d_ctasks, VA.nttasks = (int)tt.size();
@@ -333,7 +333,7 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
   void *d_temp = nullptr;
   size_t temp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, d_count, d_start, (int)(nbuckets + 1), s);
-  B200_CHECK(cudaMalloc(&d_temp, temp_bytes));
+  dev_alloc(&d_temp, temp_bytes);
   cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_count, d_start, (int)(nbuckets + 1), s);
   std::vector<unsigned int> start(nbuckets + 1);
   B200_CHECK(cudaMemcpyAsync(start.data(), d_start, (nbuckets + 1) * sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -342,12 +342,12 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
   B200_ASSERT(nvis < ((size_t)1 << 31), "too many (task, tile) visits on one level");
   cl.nvisits = (long long)nvis;
   B200_ASSERT(tt.size() < ((size_t)1 << 24), "too many tiled tasks on one level for the 24-bit visit field");
-  B200_CHECK(cudaMalloc((void **)&cl.d_visits, (nvis + 40) * sizeof(CVisit)));
+  dev_alloc(&cl.d_visits, (nvis + 40) * sizeof(CVisit));
   B200_CHECK(cudaMemsetAsync(cl.d_visits, 0, (nvis + 40) * sizeof(CVisit), s));  // (the kernels peek past the end)
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
   unsigned long long *d_keys[2] = {nullptr, nullptr};
   CVisit *d_visits_alt = nullptr;
-  B200_CHECK(cudaMalloc((void **)&d_keys[0], std::max<size_t>(nvis, 1) * sizeof(unsigned long long)));
+  dev_alloc(&d_keys[0], std::max<size_t>(nvis, 1) * sizeof(unsigned long long));
   int qbits = 1, bbits = 1;
   while (((size_t)1 << qbits) < tt.size())
     qbits++;
@@ -358,24 +358,24 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
   B200_CHECK(cudaGetLastError());
   count_launch(4);
   if (nvis > 1) {
-    B200_CHECK(cudaMalloc((void **)&d_keys[1], nvis * sizeof(unsigned long long)));
-    B200_CHECK(cudaMalloc((void **)&d_visits_alt, (nvis + 40) * sizeof(CVisit)));
+    dev_alloc(&d_keys[1], nvis * sizeof(unsigned long long));
+    dev_alloc(&d_visits_alt, (nvis + 40) * sizeof(CVisit));
     B200_CHECK(cudaMemsetAsync(d_visits_alt, 0, (nvis + 40) * sizeof(CVisit), s));
     cub::DoubleBuffer<unsigned long long> kb(d_keys[0], d_keys[1]);
     cub::DoubleBuffer<CVisit> vb(cl.d_visits, d_visits_alt);
     void *d_sort_temp = nullptr;
     size_t sort_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb, vb, (int)nvis, 0, qbits + bbits, s);
-    B200_CHECK(cudaMalloc(&d_sort_temp, std::max<size_t>(sort_bytes, 1)));
+    dev_alloc(&d_sort_temp, std::max<size_t>(sort_bytes, 1));
     cub::DeviceRadixSort::SortPairs(d_sort_temp, sort_bytes, kb, vb, (int)nvis, 0, qbits + bbits, s);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaStreamSynchronize(s));
     count_launch(6);
     if (vb.Current() != cl.d_visits)
       std::swap(cl.d_visits, d_visits_alt);
-    cudaFree(d_sort_temp);
+    dev_free(d_sort_temp);
   }
-  cudaFree(d_keys[0]), cudaFree(d_keys[1]), cudaFree(d_visits_alt);
+  dev_free(d_keys[0]), dev_free(d_keys[1]), dev_free(d_visits_alt);
 
   // work items per lp class: a tile's visits of that class (contiguous, ordered by lp) cut into chunks
   for (int cls = 0; cls < kNumClasses; cls++) {
@@ -409,7 +409,7 @@ inline void build_ctile_level(CtileLevel &cl, const int level, const LevelDev &L
     up(&cl.d_class_task_ids[cls], ids);
   }
   B200_CHECK(cudaStreamSynchronize(s));
-  cudaFree(d_temp), cudaFree(d_count), cudaFree(d_start), cudaFree(d_ttasks);
+  dev_free(d_temp), dev_free(d_count), dev_free(d_start), dev_free(d_ttasks);
 }
 
 // ---------------------------------------------------------------------------
@@ -1019,10 +1019,10 @@ struct CtileList {  // list-wide data of the CTA-tile path
   unsigned *d_zmask = nullptr;
   void release() {
     for (auto &p : d_work) {
-      cudaFree(p);
+      dev_free(p);
       p = nullptr;
     }
-    cudaFree(d_counters), cudaFree(d_zmask);
+    dev_free(d_counters), dev_free(d_zmask);
     d_counters = nullptr, d_zmask = nullptr;
     for (auto &v : level_first)
       v.clear();
@@ -1032,9 +1032,9 @@ struct CtileList {  // list-wide data of the CTA-tile path
 inline void finish_ctile_list(CtileList &cl, std::vector<CtileLevel *> &levels, cudaStream_t s) {
   cl.release();
   const std::vector<unsigned> zm = build_ct_zmask();
-  B200_CHECK(cudaMalloc((void **)&cl.d_zmask, zm.size() * sizeof(unsigned)));
+  dev_alloc(&cl.d_zmask, zm.size() * sizeof(unsigned));
   B200_CHECK(cudaMemcpyAsync(cl.d_zmask, zm.data(), zm.size() * sizeof(unsigned), cudaMemcpyHostToDevice, s));
-  B200_CHECK(cudaMalloc((void **)&cl.d_counters, 2 * kNumClasses * 8 * sizeof(int)));
+  dev_alloc(&cl.d_counters, 2 * kNumClasses * 8 * sizeof(int));
   for (int cls = 0; cls < kNumClasses; cls++) {
     std::vector<CWork> all;
     cl.level_first[cls].assign(levels.size() + 1, 0);
@@ -1045,7 +1045,7 @@ inline void finish_ctile_list(CtileList &cl, std::vector<CtileLevel *> &levels, 
       levels[l]->work[cls].shrink_to_fit();
     }
     cl.level_first[cls][levels.size()] = (int)all.size();
-    B200_CHECK(cudaMalloc((void **)&cl.d_work[cls], std::max<size_t>(all.size(), 1) * sizeof(CWork)));
+    dev_alloc(&cl.d_work[cls], std::max<size_t>(all.size(), 1) * sizeof(CWork));
     if (!all.empty())
       B200_CHECK(cudaMemcpyAsync(cl.d_work[cls], all.data(), all.size() * sizeof(CWork), cudaMemcpyHostToDevice, s));
     B200_CHECK(cudaStreamSynchronize(s));  // `all` is a temporary

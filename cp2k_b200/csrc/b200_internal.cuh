@@ -12,7 +12,10 @@
 
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <algorithm>
 #include <memory>
+#include <mutex>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 #include <cstdio>
@@ -48,6 +51,104 @@ inline void b200_fatal(const char *what, const char *detail, const char *file, c
   } while (0)
 
 namespace b200 {
+
+// Device memory of the task lists goes through a small caching arena: cudaMalloc / cudaFree of
+// GB-sized buffers cost 50-500 ms each on the boxes we measured (and vary by 5x from call to
+// call), and CP2K rebuilds a list of the same size every MD step.  Freed blocks are kept per
+// device and handed out again to requests of (nearly) the same size; the cache is dropped when
+// an allocation fails, by grid_b200_release_cache(), or beyond GRID_B200_CACHE_MB (default 16384).
+struct DevArena {
+  struct Block {
+    void *p;
+    size_t bytes;
+    int dev;
+  };
+  std::mutex mu;
+  std::vector<Block> free_blocks;
+  std::unordered_map<void *, std::pair<size_t, int>> live;
+  size_t cached_bytes = 0, cap_bytes = 0;
+  bool cap_read = false;
+
+  static size_t round_up(const size_t bytes) {
+    const size_t q = (bytes >= ((size_t)1 << 20)) ? ((size_t)2 << 20) : 512;
+    return (std::max<size_t>(bytes, 1) + q - 1) / q * q;
+  }
+  void drop_cache_locked(const int dev) {
+    size_t k = 0;
+    for (size_t i = 0; i < free_blocks.size(); i++) {
+      if (dev < 0 || free_blocks[i].dev == dev) {
+        cudaFree(free_blocks[i].p);
+        cached_bytes -= free_blocks[i].bytes;
+      } else {
+        free_blocks[k++] = free_blocks[i];
+      }
+    }
+    free_blocks.resize(k);
+  }
+  void *alloc(const size_t want) {
+    const size_t bytes = round_up(want);
+    int dev = 0;
+    B200_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    int best = -1;
+    for (int i = 0; i < (int)free_blocks.size(); i++) {
+      const Block &b = free_blocks[i];
+      if (b.dev == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 8 &&
+          (best < 0 || b.bytes < free_blocks[best].bytes))
+        best = i;
+    }
+    void *p = nullptr;
+    size_t got = bytes;
+    if (best >= 0) {
+      p = free_blocks[best].p, got = free_blocks[best].bytes;
+      cached_bytes -= got;
+      free_blocks[best] = free_blocks.back();
+      free_blocks.pop_back();
+    } else if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      drop_cache_locked(dev);
+      B200_CHECK(cudaMalloc(&p, bytes));
+    }
+    live[p] = {got, dev};
+    return p;
+  }
+  void free(void *p) {
+    if (p == nullptr)
+      return;
+    // what cudaFree does implicitly: nothing in flight may still use the block when it is reused
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lock(mu);
+    if (!cap_read) {
+      const char *env = getenv("GRID_B200_CACHE_MB");
+      cap_bytes = (size_t)(env ? atoll(env) : 16384) << 20;
+      cap_read = true;
+    }
+    auto it = live.find(p);
+    if (it == live.end()) {  // not ours (never happens inside the library)
+      cudaFree(p);
+      return;
+    }
+    const Block b{p, it->second.first, it->second.second};
+    live.erase(it);
+    if (cached_bytes + b.bytes > cap_bytes) {
+      cudaFree(p);
+    } else {
+      free_blocks.push_back(b);
+      cached_bytes += b.bytes;
+    }
+  }
+  void release() {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lock(mu);
+    drop_cache_locked(-1);
+  }
+};
+inline DevArena &dev_arena() {
+  static DevArena *a = new DevArena();  // leaked on purpose: no CUDA calls at process exit
+  return *a;
+}
+template <typename T> inline void dev_alloc(T **p, const size_t bytes) { *p = (T *)dev_arena().alloc(bytes); }
+inline void dev_free(void *p) { dev_arena().free(p); }
 
 constexpr int kMaxLSide = 8;   // max angular momentum per side after ldiffs
 constexpr int kMaxLp = 16;     // max la+lb after ldiffs

@@ -157,12 +157,12 @@ struct TiledLevel {
   unsigned char *d_ktab = nullptr;   // K+1 per (n, dj, di), 0 outside the sphere
   unsigned short *d_zmask = nullptr; // [kZmRows][kZmPitch]
   void release() {
-    cudaFree(d_ttasks), cudaFree(d_pairs), cudaFree(d_work), cudaFree(d_khead), cudaFree(d_ktab);
-    cudaFree(d_zmask);
-    cudaFree(d_counters);
+    dev_free(d_ttasks), dev_free(d_pairs), dev_free(d_work), dev_free(d_khead), dev_free(d_ktab);
+    dev_free(d_zmask);
+    dev_free(d_counters);
     d_counters = nullptr;
     for (auto &p : d_class_task_ids) {
-      cudaFree(p);
+      dev_free(p);
       p = nullptr;
     }
     d_ttasks = nullptr, d_pairs = nullptr, d_work = nullptr, d_khead = nullptr, d_ktab = nullptr;
@@ -364,9 +364,28 @@ struct CreateTimer {
   }
 };
 
+// Device scratch of the per-level builders, kept across the levels of one list: GB-sized
+// cudaMalloc / cudaFree pairs cost ~100 ms each at H2O-1024 size.
+struct BuilderScratch {
+  void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[6] = {0, 0, 0, 0, 0, 0};
+  void *get(const int slot, const size_t bytes) {
+    if (bytes > cap[slot]) {
+      dev_free(p[slot]);
+      dev_alloc(&p[slot], std::max<size_t>(bytes, 16));
+      cap[slot] = bytes;
+    }
+    return p[slot];
+  }
+  ~BuilderScratch() {
+    for (auto q : p)
+      dev_free(q);
+  }
+};
+
 inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &tasks,
                               const TaskDev *d_tasks, const int first, const int last,
-                              std::vector<int> &generic_ids, cudaStream_t s) {
+                              std::vector<int> &generic_ids, BuilderScratch &scratch, cudaStream_t s) {
   CreateTimer tm(s);
   tl.release();
   const double h[3] = {L.dh[0], L.dh[4], L.dh[8]};
@@ -375,13 +394,18 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
             nbz = (L.npts_local[2] + kBZ - 1) / kBZ;
   const size_t nblocks = (size_t)nbx * nby * nbz;
 
-  // Select the tasks of the tiled path (two parallel passes over the level's records:
-  // classify, then compact in task order -- the result does not depend on the thread count).
+  // Select the tasks of the tiled path and lay them out sorted by lp class (a task's coefficient
+  // slot is then pure arithmetic on its index): two parallel passes over the level's records --
+  // classify, then write each record to its final position -- with a serial prefix over one byte
+  // per task in between; the result does not depend on the thread count.
   std::vector<TTask> tt;
+  std::vector<KTabHeader> heads;
+  std::vector<unsigned char> ktab;
   int max_n = 0, max_lp0 = 0, max_nb = 0;
   {
     const int nt = last - first;
-    std::vector<int> nidx(std::max(nt, 1));  // radius index, 0 = generic path
+    std::vector<int> nidx(std::max(nt, 1));            // radius index, 0 = generic path
+    std::vector<unsigned char> cls(std::max(nt, 1));   // lp class of a tiled task
 #pragma omp parallel for schedule(static) reduction(max : max_n, max_lp0, max_nb)
     for (int k = 0; k < nt; k++) {
       const TaskDev &T = tasks[first + k];
@@ -396,19 +420,44 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
           ok = ok && (-T.lb_cube[d] <= kTiledMaxNb);
       }
       nidx[k] = ok ? n : 0;
+      cls[k] = ok ? (unsigned char)lp_class(T.la_max + T.lb_max) : 0;
       if (ok) {
         max_n = std::max(max_n, n), max_lp0 = std::max(max_lp0, T.la_max + T.lb_max);
         for (int d = 0; d < 3; d++)
           max_nb = std::max(max_nb, -T.lb_cube[d]);
       }
     }
-    std::vector<int> pos(std::max(nt, 1));  // position of task k among the tiled (or the generic) ones
-    int n_tiled = 0, n_generic = 0;
-    for (int k = 0; k < nt; k++)
-      pos[k] = nidx[k] ? n_tiled++ : n_generic++;
-    tt.resize(n_tiled);
+    for (int c = 0; c <= kNumClasses; c++)
+      tl.class_tt_first[c] = 0;
+    int n_generic = 0;
+    for (int k = 0; k < nt; k++) {
+      if (nidx[k])
+        tl.class_tt_first[cls[k] + 1]++;
+      else
+        n_generic++;
+    }
+    for (int c = 0; c < kNumClasses; c++)
+      tl.class_tt_first[c + 1] += tl.class_tt_first[c];
+    std::vector<int> pos(std::max(nt, 1));  // final position among the tiled (or the generic) tasks
+    {
+      int next[kNumClasses], next_generic = 0;
+      for (int c = 0; c < kNumClasses; c++)
+        next[c] = tl.class_tt_first[c];
+      for (int k = 0; k < nt; k++)
+        pos[k] = nidx[k] ? next[cls[k]]++ : next_generic++;
+    }
+    const int n_tiled = tl.class_tt_first[kNumClasses];
+    tl.ntasks_tiled = n_tiled;
+    tl.max_lp0 = max_lp0;
+    tl.max_n = max_n;
+    tl.max_nb = max_nb;
     const size_t g0 = generic_ids.size();
     generic_ids.resize(g0 + n_generic);
+    if (n_tiled > 0) {
+      tt.resize(n_tiled);
+      tl.h_tt_task.resize(n_tiled);
+      build_ktabs(L, max_n, heads, ktab);
+    }
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < nt; k++) {
       const int it = first + k;
@@ -426,53 +475,24 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
       X.n = nidx[k], X.lp0 = T.la_max + T.lb_max, X.task = it;
       X.zl2 = T.zetp * 1.4426950408889634074;
       X.pad[0] = X.pad[1] = X.pad[2] = 0;
+      // the cube bounds stored with the task must agree with the table's
+      B200_ASSERT(heads[X.n].offset >= 0 && X.nb[0] == heads[X.n].nbx && X.nb[1] == heads[X.n].nby &&
+                      X.nb[2] == heads[X.n].nbz,
+                  "cube bounds disagree with the sphere table");
       tt[pos[k]] = X;
+      tl.h_tt_task[pos[k]] = it;
     }
   }
-  tl.ntasks_tiled = (int)tt.size();
-  tl.max_lp0 = max_lp0;
-  tl.max_n = max_n;
-  tl.max_nb = max_nb;
-  tm.tick("level: select tasks");
+  tm.tick("level: select tasks, K tables");
   if (tt.empty())
     return;
-  // class-sorted: a task's coefficient slot is then pure arithmetic on its index
-  {  // stable partition by lp class (three classes: one counting pass instead of a sort)
-    std::vector<TTask> sorted(tt.size());
-    size_t pos[kNumClasses + 1] = {0, 0, 0, 0};
-    for (const TTask &X : tt)
-      pos[lp_class(X.lp0) + 1]++;
-    for (int c = 0; c < kNumClasses; c++)
-      pos[c + 1] += pos[c];
-    for (const TTask &X : tt)
-      sorted[pos[lp_class(X.lp0)]++] = X;
-    tt.swap(sorted);
-  }
-  tl.h_tt_task.resize(tt.size());
-  for (int c = 0; c <= kNumClasses; c++)
-    tl.class_tt_first[c] = 0;
-  for (size_t q = 0; q < tt.size(); q++) {
-    tl.h_tt_task[q] = tt[q].task;
-    tl.class_tt_first[lp_class(tt[q].lp0) + 1]++;
-  }
-  for (int c = 0; c < kNumClasses; c++)
-    tl.class_tt_first[c + 1] += tl.class_tt_first[c];
   B200_ASSERT(nblocks * kLpBuckets * kNumClasses < (size_t)1 << 31, "too many grid blocks");
-
-  std::vector<KTabHeader> heads;
-  std::vector<unsigned char> ktab;
-  build_ktabs(L, max_n, heads, ktab);
-  for (const TTask &X : tt)  // the cube bounds stored with the task must agree with the table's
-    B200_ASSERT(heads[X.n].offset >= 0 && X.nb[0] == heads[X.n].nbx && X.nb[1] == heads[X.n].nby &&
-                    X.nb[2] == heads[X.n].nbz,
-                "cube bounds disagree with the sphere table");
   auto up = [&](auto **dst, const auto &vec) {
     using T = typename std::remove_reference<decltype(vec)>::type::value_type;
-    B200_CHECK(cudaMalloc((void **)dst, std::max<size_t>(vec.size(), 1) * sizeof(T)));
+    dev_alloc(dst, std::max<size_t>(vec.size(), 1) * sizeof(T));
     if (!vec.empty())
       B200_CHECK(cudaMemcpyAsync(*dst, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   };
-  tm.tick("level: class sort, K tables");
   up(&tl.d_ttasks, tt);
   up(&tl.d_khead, heads);
   up(&tl.d_ktab, ktab);
@@ -483,8 +503,8 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
   // pairs: count, scan, fill
   const size_t nbuckets = nblocks * kLpBuckets * kNumClasses;
   unsigned int *d_count = nullptr, *d_start = nullptr;
-  B200_CHECK(cudaMalloc((void **)&d_count, (nbuckets + 1) * sizeof(unsigned int)));
-  B200_CHECK(cudaMalloc((void **)&d_start, (nbuckets + 1) * sizeof(unsigned int)));
+  d_count = (unsigned int *)scratch.get(0, (nbuckets + 1) * sizeof(unsigned int));
+  d_start = (unsigned int *)scratch.get(1, (nbuckets + 1) * sizeof(unsigned int));
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
   PairGenArgs PA;
   PA.ttasks = tl.d_ttasks, PA.nttasks = (int)tt.size();
@@ -500,7 +520,7 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
   void *d_temp = nullptr;
   size_t temp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, d_count, d_start, (int)(nbuckets + 1), s);
-  B200_CHECK(cudaMalloc(&d_temp, temp_bytes));
+  d_temp = scratch.get(2, temp_bytes);
   cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_count, d_start, (int)(nbuckets + 1), s);
   std::vector<unsigned int> start(nbuckets + 1);
   B200_CHECK(cudaMemcpyAsync(start.data(), d_start, (nbuckets + 1) * sizeof(unsigned int),
@@ -510,11 +530,13 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
   tm.tick("level: count pairs, scan");
   B200_ASSERT(npairs < ((size_t)1 << 31), "too many (task, block) pairs on one level");
   tl.npairs = (long long)npairs;
-  B200_CHECK(cudaMalloc((void **)&tl.d_pairs, (npairs + kPairPad) * sizeof(TPair)));
+  dev_alloc(&tl.d_pairs, (npairs + kPairPad) * sizeof(TPair));
   B200_CHECK(cudaMemsetAsync(d_count, 0, (nbuckets + 1) * sizeof(unsigned int), s));
   unsigned long long *d_keys[2] = {nullptr, nullptr};
   TPair *d_pairs_alt = nullptr;
-  B200_CHECK(cudaMalloc((void **)&d_keys[0], std::max<size_t>(npairs, 1) * sizeof(unsigned long long)));
+  // both key buffers, the second pair buffer and the sort's temporary storage share slots 3..5
+  d_keys[0] = (unsigned long long *)scratch.get(3, 2 * std::max<size_t>(npairs, 1) * sizeof(unsigned long long));
+  d_keys[1] = d_keys[0] + std::max<size_t>(npairs, 1);
   int qbits = 1, bbits = 1;
   while (((size_t)1 << qbits) < tt.size())
     qbits++;
@@ -529,23 +551,20 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
   // coefficients are shared through L1/L2 instead of being re-read from HBM; it
   // also makes the accumulation order (and so the results) reproducible.
   if (npairs > 1) {
-    B200_CHECK(cudaMalloc((void **)&d_keys[1], npairs * sizeof(unsigned long long)));
-    B200_CHECK(cudaMalloc((void **)&d_pairs_alt, (npairs + kPairPad) * sizeof(TPair)));
+    d_pairs_alt = (TPair *)scratch.get(4, (npairs + kPairPad) * sizeof(TPair));
     cub::DoubleBuffer<unsigned long long> kb(d_keys[0], d_keys[1]);
     cub::DoubleBuffer<uint4> vb((uint4 *)tl.d_pairs, (uint4 *)d_pairs_alt);
     void *d_sort_temp = nullptr;
     size_t sort_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, kb, vb, (int)npairs, 0, qbits + bbits, s);
-    B200_CHECK(cudaMalloc(&d_sort_temp, std::max<size_t>(sort_bytes, 1)));
+    d_sort_temp = scratch.get(5, std::max<size_t>(sort_bytes, 1));
     cub::DeviceRadixSort::SortPairs(d_sort_temp, sort_bytes, kb, vb, (int)npairs, 0, qbits + bbits, s);
     B200_CHECK(cudaGetLastError());
     B200_CHECK(cudaStreamSynchronize(s));
     count_launch(6);
-    if ((TPair *)vb.Current() != tl.d_pairs)
-      std::swap(tl.d_pairs, d_pairs_alt);
-    cudaFree(d_sort_temp);
+    if ((TPair *)vb.Current() != tl.d_pairs)  // the sorted pairs ended up in the scratch buffer
+      B200_CHECK(cudaMemcpyAsync(tl.d_pairs, d_pairs_alt, npairs * sizeof(TPair), cudaMemcpyDeviceToDevice, s));
   }
-  cudaFree(d_keys[0]), cudaFree(d_keys[1]), cudaFree(d_pairs_alt);
   if (npairs > 0)
     for (int i = 0; i < kPairPad; i++)
       B200_CHECK(cudaMemcpyAsync(tl.d_pairs + npairs + i, tl.d_pairs + npairs - 1, sizeof(TPair),
@@ -583,19 +602,19 @@ inline void build_tiled_level(TiledLevel &tl, const LevelDev &L, const TaskVec &
   }
   tl.class_work_first[kNumClasses] = (int)work.size();
   // TaskDev ids per class (for calls whose l growth pushes a class out of the tiled range)
+  // (the tiled tasks are class-sorted: a class's ids are a slice of h_tt_task)
   for (int cls = 0; cls < kNumClasses; cls++) {
-    std::vector<int> ids;
-    for (const TTask &X : tt)
-      if (lp_class(X.lp0) == cls)
-        ids.push_back(X.task);
-    tl.class_ntasks[cls] = (int)ids.size();
-    up(&tl.d_class_task_ids[cls], ids);
+    const int f = tl.class_tt_first[cls], n = tl.class_tt_first[cls + 1] - f;
+    tl.class_ntasks[cls] = n;
+    dev_alloc(&tl.d_class_task_ids[cls], std::max<size_t>(n, 1) * sizeof(int));
+    if (n > 0)
+      B200_CHECK(cudaMemcpyAsync(tl.d_class_task_ids[cls], tl.h_tt_task.data() + f, n * sizeof(int),
+                                 cudaMemcpyHostToDevice, s));
   }
   tl.nwork = (int)work.size();
   up(&tl.d_work, work);
-  B200_CHECK(cudaMalloc((void **)&tl.d_counters, 2 * kNumClasses * 4 * sizeof(int)));
+  dev_alloc(&tl.d_counters, 2 * kNumClasses * 4 * sizeof(int));
   B200_CHECK(cudaStreamSynchronize(s));
-  cudaFree(d_temp), cudaFree(d_count), cudaFree(d_start);
   tm.tick("level: work items");
 }
 
@@ -1258,8 +1277,8 @@ inline void compute_stats(const TaskDev *d_tasks, const int ntasks, const std::v
   (void)h_tasks;
   LevelDev *d_levels = nullptr;
   double *d_out = nullptr;
-  B200_CHECK(cudaMalloc((void **)&d_levels, levels.size() * sizeof(LevelDev)));
-  B200_CHECK(cudaMalloc((void **)&d_out, 3 * sizeof(double)));
+  dev_alloc(&d_levels, levels.size() * sizeof(LevelDev));
+  dev_alloc(&d_out, 3 * sizeof(double));
   B200_CHECK(cudaMemcpyAsync(d_levels, levels.data(), levels.size() * sizeof(LevelDev),
                              cudaMemcpyHostToDevice, s));
   B200_CHECK(cudaMemsetAsync(d_out, 0, 3 * sizeof(double), s));
@@ -1271,8 +1290,8 @@ inline void compute_stats(const TaskDev *d_tasks, const int ntasks, const std::v
   B200_CHECK(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, s));
   B200_CHECK(cudaStreamSynchronize(s));
   stats[4] = h[0], stats[5] = h[1], stats[6] = h[2];
-  cudaFree(d_levels);
-  cudaFree(d_out);
+  dev_free(d_levels);
+  dev_free(d_out);
 }
 
 }  // namespace b200

@@ -120,8 +120,8 @@ template <typename T> struct DevBuf {
     if (n <= cap)
       return;
     if (p)
-      B200_CHECK(cudaFree(p));
-    B200_CHECK(cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(T)));
+      dev_free(p);
+    dev_alloc(&p, std::max<size_t>(n, 1) * sizeof(T));
     cap = n;
   }
   template <class Vec> void upload(const Vec &v, cudaStream_t s) {
@@ -133,7 +133,7 @@ template <typename T> struct DevBuf {
   }
   void release() {
     if (p)
-      cudaFree(p);
+      dev_free(p);
     p = nullptr, cap = 0;
   }
 };
@@ -785,6 +785,7 @@ static void build_task_list(
   // split every level into tiled-path and generic-path tasks
   tl.h_generic_ids.clear();
   tl.generic_first.assign(nlevels + 1, 0);
+  BuilderScratch tiled_scratch;
   for (int l = 0; l < nlevels; l++) {
     LevelInfo &li = tl.linfo[l];
     std::vector<int> generic_ids;
@@ -795,7 +796,8 @@ static void build_task_list(
       build_ctile_level(li.ctile, l, tl.levels[l], tl.h_tasks, li.first, li.last, generic_ids, item_cap, s);
     }
     else
-      build_tiled_level(li.tiled, tl.levels[l], tl.h_tasks, tl.d_tasks.p, li.first, li.last, generic_ids, s);
+      build_tiled_level(li.tiled, tl.levels[l], tl.h_tasks, tl.d_tasks.p, li.first, li.last, generic_ids,
+                        tiled_scratch, s);
     li.n_generic = (int)generic_ids.size();
     tl.generic_first[l] = (int)tl.h_generic_ids.size();
     tl.h_generic_ids.insert(tl.h_generic_ids.end(), generic_ids.begin(), generic_ids.end());
@@ -916,6 +918,8 @@ void grid_b200_create_task_list(
                   radius_list, rab_list, npts_global, npts_local, shift_local, border_width, dh,
                   dh_inv);
 }
+
+void grid_b200_release_cache(void) { dev_arena().release(); }
 
 void grid_b200_free_task_list(grid_b200_task_list *ptr) {
   if (ptr == nullptr)

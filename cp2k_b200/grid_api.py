@@ -336,6 +336,8 @@ class B200Library(GridLibrary):
         L.grid_b200_set_stream.restype = None
         L.grid_b200_get_launch_count.argtypes = []
         L.grid_b200_get_launch_count.restype = C.c_longlong
+        L.grid_b200_release_cache.argtypes = []
+        L.grid_b200_release_cache.restype = None
         L.grid_b200_device_count.argtypes = []
         L.grid_b200_device_count.restype = C.c_int
         L.grid_b200_set_kernel_variant.argtypes = [C.c_int]
@@ -493,6 +495,10 @@ class B200Library(GridLibrary):
 
     def launch_count(self) -> int:
         return int(self.lib.grid_b200_get_launch_count())
+
+    def release_cache(self) -> None:
+        """Return the device blocks freed task lists left in the library's arena to the driver."""
+        self.lib.grid_b200_release_cache()
 
     def device_count(self) -> int:
         return int(self.lib.grid_b200_device_count())

@@ -227,6 +227,13 @@ void grid_b200_set_kernel_variant(const int variant);
  * gpu/grid_gpu_context.cu:538-552 does. */
 void grid_b200_get_task_counts(const grid_b200_task_list *task_list, int ortho[20], int general[20]);
 
+/* Task lists take their device memory from a caching arena (cudaMalloc / cudaFree of GB-sized
+ * tables cost more than building them, and CP2K rebuilds a list of the same size every MD step):
+ * freed blocks are kept, up to GRID_B200_CACHE_MB (environment, default 16384), and reused by the
+ * next create.  This returns the cached blocks to the driver (the library does so itself when an
+ * allocation fails).  No counterpart in the reference. */
+void grid_b200_release_cache(void);
+
 /* Number of CUDA kernels launched by this library since load. */
 long long grid_b200_get_launch_count(void);
 
