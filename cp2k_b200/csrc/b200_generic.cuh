@@ -14,8 +14,9 @@
 //   * the (y,z) contraction is done once per cube row by one thread, the row is
 //     then swept by a half-warp with coalesced accesses along x;
 //   * integrate walks the cube ONCE for all coefficients (no lbatch passes):
-//     per-row partial sums are reduced by warp shuffles and folded into the
-//     coefficients by all threads in parallel.
+//     per-row partial sums are reduced by shuffles inside groups of eight lanes
+//     (four rows per warp) and folded into the coefficients in two stages
+//     (rows -> (lx, ly) sums per cube plane -> coefficients), by all threads.
 #pragma once
 #include "b200_coef.cuh"
 
@@ -23,6 +24,8 @@ namespace b200 {
 
 constexpr int kGenThreads = 128;
 constexpr int kGenRows = 128;  // cube rows per chunk (one per thread)
+constexpr int kGenU = 1024;    // integrate: (plane, lx, ly) partial sums per fold batch
+constexpr int kGenPairs = (kMaxLp + 1) * (kMaxLp + 2) / 2;
 
 __device__ inline int pair_dist(const int k) { return (k <= 0) ? -k : k - 1; }
 
@@ -40,7 +43,8 @@ struct GenSmem {
 __host__ __device__ inline size_t gen_smem_bytes(const int max_lp, const int max_w) {
   const size_t nd = (size_t)ncoset(max_lp) + 3 * (size_t)(max_lp + 1) * max_w +
                     (size_t)kGenRows * (max_lp + 1) + 2 * (size_t)kGenRows;
-  return nd * sizeof(double) + (4 * (size_t)kGenRows + (size_t)max_w) * sizeof(int);
+  return nd * sizeof(double) + (4 * (size_t)kGenRows + (size_t)((max_w + 1) & ~1)) * sizeof(int) +
+         kGenU * sizeof(double) + kGenPairs * sizeof(int);
 }
 
 template <bool COLLOCATE>
@@ -69,6 +73,9 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
   double *s_aux = s_row + kGenRows * (L.max_lp + 1);
   int *s_info = (int *)(s_aux + 2 * kGenRows);
   int *s_map = s_info + 4 * kGenRows;
+  // (the map is padded to an even number of ints so that the doubles behind it stay aligned)
+  double *s_u = (double *)(s_map + ((W + 1) & ~1));
+  int *s_pair = (int *)(s_u + kGenU);
 
   const LevelDev &G = L.level;
   const bool ortho = T.use_ortho;
@@ -119,17 +126,24 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
   const double *tabx = s_tab, *taby = s_tab + (size_t)lp1 * W,
                *tabz = s_tab + (size_t)2 * lp1 * W;
 
-  // integrate: per-thread coefficient accumulators
-  const int ngroups = (nc <= kGenThreads) ? kGenThreads / nc : 1;
+  // integrate: per-thread coefficient accumulators (coefficient tid + m * kGenThreads)
   constexpr int kCPT = 8;  // ncoset(16) = 969 <= 8 * 128
   double acc[kCPT];
   for (int m = 0; m < kCPT; m++)
     acc[m] = 0.0;
-  const int my_c = (nc <= kGenThreads) ? tid % nc : tid;
-  const int my_g = (nc <= kGenThreads) ? tid / nc : 0;
+  // (lx, ly) pairs with lx + ly <= lp, pair index = ly * lp1 - ly (ly - 1) / 2 + lx
+  const int npairs = lp1 * (lp1 + 1) / 2;
+  if (!COLLOCATE)
+    for (int q = tid; q < lp1 * lp1; q += kGenThreads) {
+      const int ly = q / lp1, lx = q % lp1;
+      if (lx + ly <= lp)
+        s_pair[ly * lp1 - (ly * (ly - 1)) / 2 + lx] = lx | (ly << 8);
+    }
 
   const int nrows = w[1] * w[2];
-  const int hw = tid >> 4, sub = tid & 15;
+  // collocate: half-warps sweep a row; integrate: groups of eight lanes
+  constexpr int kLanes = COLLOCATE ? 16 : 8;
+  const int hw = tid / kLanes, sub = tid % kLanes;
   const int ny = G.npts_local[1], nx = G.npts_local[0];
 
   for (int r0 = 0; r0 < nrows; r0 += kGenRows) {
@@ -215,7 +229,7 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
 
     // ---- phase B: half-warps sweep the rows along x --------------------------
     const int nr = min(kGenRows, nrows - r0);
-    for (int r = hw; r < nr; r += kGenThreads / 16) {
+    for (int r = hw; r < nr; r += kGenThreads / kLanes) {
       const int base = s_info[4 * r + 0];
       if (base < 0)
         continue;
@@ -243,18 +257,18 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
           }
         }
       } else {
-        // integrate: cr[l] = sum_i grid[i] * p_l(i), reduced over the half-warp.
-        // Only lane `sub == 0` of the half-warp ever touches cr[] here.
-        const unsigned hmask = 0xffffu << (16 * ((tid >> 4) & 1));
+        // integrate: cr[l] = sum_i grid[i] * p_l(i), reduced over the group of eight lanes.
+        // Only lane `sub == 0` of the group ever touches cr[] here.
+        const unsigned hmask = 0xffu << (8 * ((tid >> 3) & 3));
         if (sub == 0)
           for (int l = 0; l <= lp; l++)
             cr[l] = 0.0;
-        for (int ib = i0; ib <= i1; ib += 64) {
+        for (int ib = i0; ib <= i1; ib += 32) {
           double gv[4], xv[4];
           int gi[4];
 #pragma unroll
           for (int m = 0; m < 4; m++) {
-            const int i = ib + sub + 16 * m;
+            const int i = ib + sub + 8 * m;
             gv[m] = 0.0, xv[m] = 0.0, gi[m] = 0;
             if (i <= i1) {
               if (ortho) {
@@ -284,8 +298,9 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
                 pw[m] *= xv[m];
               }
             }
-            for (int o = 8; o > 0; o >>= 1)
-              part += __shfl_xor_sync(hmask, part, o, 16);
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1)
+              part += __shfl_xor_sync(hmask, part, o, 8);
             if (sub == 0)
               cr[l] += part;
           }
@@ -296,54 +311,48 @@ __global__ void __launch_bounds__(kGenThreads) generic_kernel(const GridLaunch L
     if (!COLLOCATE) {
       __syncthreads();
       // ---- phase A': fold the row sums into the coefficients ----------------
-      if (nc <= kGenThreads) {
-        if (my_g < ngroups) {
-          const Orb o = orb_of(s_orb, my_c);
-          for (int r = my_g; r < nr; r += ngroups) {
-            if (s_info[4 * r] < 0)
-              continue;
-            const int kj = s_info[4 * r + 3];
-            acc[0] += s_row[r * lp1 + o.l[0]] * taby[o.l[1] * W + (kj & 0xffff)] *
-                      tabz[o.l[2] * W + (kj >> 16)];
-          }
+      // Two stages per batch of cube planes kk: u[kk][lx,ly] = sum_jj row[kk,jj][lx] taby[ly][jj],
+      // then coef[lx,ly,lz] += sum_kk u[kk][lx,ly] tabz[lz][kk]  (rows x pairs + planes x ncoset
+      // operations instead of rows x ncoset).
+      const int kk_first = r0 / w[1], kk_last = (r0 + nr - 1) / w[1];
+      const int kbatch = max(1, kGenU / npairs);
+      for (int kb0 = kk_first; kb0 <= kk_last; kb0 += kbatch) {
+        const int nkb = min(kbatch, kk_last - kb0 + 1);
+        for (int item = tid; item < nkb * npairs; item += kGenThreads) {
+          const int kb = item / npairs, pr = item - kb * npairs;
+          const int lx = s_pair[pr] & 0xff, ly = s_pair[pr] >> 8;
+          const int kk = kb0 + kb;
+          const int ra = max(kk * w[1] - r0, 0), rb = min((kk + 1) * w[1] - r0, nr);
+          double u = 0.0;
+          for (int r = ra; r < rb; r++)
+            if (s_info[4 * r] >= 0)
+              u += s_row[r * lp1 + lx] * taby[ly * W + (r0 + r - kk * w[1])];
+          s_u[item] = u;
         }
-      } else {
+        __syncthreads();
+#pragma unroll
         for (int m = 0; m < kCPT; m++) {
           const int c = tid + m * kGenThreads;
-          if (c >= nc)
-            break;
-          const Orb o = orb_of(s_orb, c);
-          for (int r = 0; r < nr; r++) {
-            if (s_info[4 * r] < 0)
-              continue;
-            const int kj = s_info[4 * r + 3];
-            acc[m] += s_row[r * lp1 + o.l[0]] * taby[o.l[1] * W + (kj & 0xffff)] *
-                      tabz[o.l[2] * W + (kj >> 16)];
+          if (c < nc) {
+            const Orb o = orb_of(s_orb, c);
+            const int pr = o.l[1] * lp1 - (o.l[1] * (o.l[1] - 1)) / 2 + o.l[0];
+            double a = acc[m];
+            for (int kb = 0; kb < nkb; kb++)
+              a += s_u[kb * npairs + pr] * tabz[o.l[2] * W + kb0 + kb];
+            acc[m] = a;
           }
         }
+        __syncthreads();
       }
     }
   }
 
   if (!COLLOCATE) {
-    __syncthreads();
-    if (nc <= kGenThreads) {
-      double *red = s_row;  // ngroups * nc <= 128 doubles
-      if (my_g < ngroups)
-        red[my_g * nc + my_c] = acc[0];
-      __syncthreads();
-      if (tid < nc) {
-        double v = 0.0;
-        for (int g = 0; g < ngroups; g++)
-          v += red[g * nc + tid];
-        coef_g[tid] = v;
-      }
-    } else {
-      for (int m = 0; m < kCPT; m++) {
-        const int c = tid + m * kGenThreads;
-        if (c < nc)
-          coef_g[c] = acc[m];
-      }
+#pragma unroll
+    for (int m = 0; m < kCPT; m++) {
+      const int c = tid + m * kGenThreads;
+      if (c < nc)
+        coef_g[c] = acc[m];
     }
   }
 }
