@@ -348,6 +348,10 @@ def main():
                     help="skip the reference-CUDA-backend leg of the N=1 line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--allreduce", default="after", choices=["after", "fused", "peer"],
+                    help="replicated grids (--decomp blocks, --halo library): sum over the ranks as one grouped NCCL "
+                         "all-reduce between collocate and integrate (default), as per-level NCCL all-reduces inside "
+                         "the collocate call, or through NVLink peer memory on the copy engines inside the call")
     ap.add_argument("--decomp", default="blocks", choices=["blocks", "slab"],
                     help="multi-GPU decomposition: matrix blocks + replicated grids + all-reduce (default), "
                          "or z-slab rs_grids + NCCL halo sum/fill (cp2k_b200/rsgrid.py)")
@@ -417,6 +421,15 @@ def main():
         halo_comm = rsgrid.HaloComm(lib, rank, world, dist) if args.halo == "library" else None
     else:
         wl = split_blocks(wl_full, world, rank)
+    # replicated grids: the library sums each level over the ranks inside the collocate call
+    # (a level's NCCL all-reduce behind its kernels, overlapping the other levels' kernels)
+    fused_reduce = (world > 1 and slab_levels is None and args.halo == "library" and args.allreduce in ("fused", "peer"))
+    if world > 1 and slab_levels is None and args.halo == "library":
+        from cp2k_b200 import rsgrid
+
+        halo_comm = rsgrid.HaloComm(lib, rank, world, dist, stream_ptr=torch.cuda.current_stream().cuda_stream)
+        if fused_reduce:
+            halo_comm.set_collocate_reduce(True)
     torch.cuda.synchronize()
     free0 = torch.cuda.mem_get_info()[0]
     # create is host-heavy (sorting, table building) and the box's host cores are noisy: three
@@ -447,18 +460,30 @@ def main():
     pab = OffloadBuffer.with_device(wl.pab_len)
     pab.device.copy_(torch.from_numpy(pab_h.host))
     pab.host[:] = pab_h.host
-    grids = [OffloadBuffer.with_device(l.npts_local_total) for l in wl.layouts]
+    grids, peer_memory = None, False
+    if fused_reduce and args.allreduce == "peer":
+        # the grids of all ranks in NVLink peer memory: the sum over the ranks runs on the copy
+        # engines beside the other levels' kernels (grid_b200_comm_reduce_grid)
+        shared = halo_comm.share_grids([l.npts_local_total for l in wl.layouts])
+        if shared is not None:
+            grids = [OffloadBuffer(l.npts_local_total, pinned=True, device=t) for l, t in zip(wl.layouts, shared)]
+            peer_memory = True
+    if grids is None:
+        grids = [OffloadBuffer.with_device(l.npts_local_total) for l in wl.layouts]
     hab = OffloadBuffer.with_device(wl.pab_len)
     forces = np.zeros((wl.natoms, 3)) if args.forces else None
     virial = np.zeros((3, 3)) if args.virial else None
 
     def exchange(gs):
         """The exchange step between collocate and integrate."""
-        if world == 1:
+        if world == 1 or fused_reduce:
             return
         if slab_levels is None:
-            for g in gs:
-                dist.all_reduce(g.device)
+            if halo_comm is not None:  # the four levels as one grouped NCCL operation
+                halo_comm.allreduce_levels([g.device for g in gs], torch.cuda.current_stream().cuda_stream)
+            else:
+                for g in gs:
+                    dist.all_reduce(g.device)
             return
         if halo_comm is not None:
             # the library's exchange: ONE grouped NCCL send/recv (+ all-reduce of the replicated
@@ -655,6 +680,8 @@ def main():
                 dist.all_reduce(hab.device)
         torch.cuda.synchronize()
         # the reference: this rank alone on the whole task list
+        if fused_reduce:
+            halo_comm.set_collocate_reduce(False)
         tl1 = wl_full.create(lib)
         pab1 = OffloadBuffer.with_device(wl_full.pab_len)
         pab1.device.copy_(torch.from_numpy(pab_full.host))
@@ -738,6 +765,10 @@ def main():
             # (all-reduce, or halo sum + fill) and the owner reduction of H
             "exchange_ms_per_step": (ms_per_step - sum(v[0] for v in tm.values()) / args.steps) if world > 1 else 0.0,
             "exchange_pieces_ms": exchange_ms if world > 1 else None,
+            "grid_sum": (("peer memory (copy engines + step flags), inside collocate" if peer_memory else
+                          "NCCL all-reduce per level, inside collocate") if fused_reduce else
+                         ("between the calls: " + ("library NCCL, all levels in one group" if halo_comm is not None
+                                                   else "torch.distributed") if world > 1 else None)),
             "create_task_list": {"ms": create_ms, "all_ms": create_all_ms,
                                  "device_bytes": int(table_bytes),
                                  "in_steps": create_ms / ms_per_step},

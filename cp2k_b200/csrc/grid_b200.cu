@@ -921,6 +921,9 @@ void grid_b200_create_task_list(
 
 void grid_b200_release_cache(void) { dev_arena().release(); }
 
+static grid_b200_comm *g_collocate_comm = nullptr;
+void grid_b200_set_collocate_reduce(grid_b200_comm *comm) { g_collocate_comm = comm; }
+
 void grid_b200_free_task_list(grid_b200_task_list *ptr) {
   if (ptr == nullptr)
     return;
@@ -945,10 +948,16 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   }
   if (tl.empty) {  // grid_task_list.c:185-189
     for (int l = 0; l < nlevels; l++) {
+      if (g_collocate_comm != nullptr && g_device_resident && use_caller_device(grids[l]))
+        grid_b200_comm_begin_grid(g_collocate_comm, grids[l]->device_buffer, (void *)s);
       if (g_device_resident && use_caller_device(grids[l]))
         B200_CHECK(cudaMemsetAsync(grids[l]->device_buffer, 0, grids[l]->size, s));
       else
         memset(grids[l]->host_buffer, 0, grids[l]->size);
+      if (g_collocate_comm != nullptr) {  // the other ranks' lists need not be empty
+        B200_ASSERT(g_device_resident && use_caller_device(grids[l]), "the collocate reduction needs device-resident grids");
+        grid_b200_comm_reduce_grid(g_collocate_comm, grids[l]->device_buffer, grids[l]->size / sizeof(double), (void *)s);
+      }
     }
     return;
   }
@@ -1023,6 +1032,8 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
         d_grid = tl.d_grids[l].p;
       }
       dg[l] = d_grid, cl[l] = &tl.linfo[l].ctile;
+      if (g_collocate_comm != nullptr)
+        grid_b200_comm_begin_grid(g_collocate_comm, d_grid, (void *)s);
       B200_CHECK(cudaMemsetAsync(d_grid, 0, npts * sizeof(double), s));
     }
     CtileCall C;
@@ -1043,6 +1054,13 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
           launch_generic(GL, true);
         }
     }
+    if (g_collocate_comm != nullptr)
+      for (int l = 0; l < nlevels; l++) {
+        const LevelDev &L = tl.levels[l];
+        B200_ASSERT(g_device_resident && use_caller_device(grids[l]), "the collocate reduction needs device-resident grids");
+        grid_b200_comm_reduce_grid(g_collocate_comm, dg[l], (size_t)L.npts_local[0] * L.npts_local[1] * L.npts_local[2],
+                                   (void *)s);
+      }
     delete tm_grid;
     for (int l = 0; l < nlevels; l++) {
       const bool resident = g_device_resident && use_caller_device(grids[l]);
@@ -1077,6 +1095,8 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
     }
     cudaStream_t ls = tl.level_streams[l];
     B200_CHECK(cudaStreamWaitEvent(ls, tl.ev_fork, 0));
+    if (g_collocate_comm != nullptr)
+      grid_b200_comm_begin_grid(g_collocate_comm, d_grid, (void *)ls);
     B200_CHECK(cudaMemsetAsync(d_grid, 0, npts * sizeof(double), ls));
     const bool force_generic = (g_variant == 1);
     GridLaunch GL;
@@ -1097,6 +1117,10 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
             launch_generic(GL, true);
           }
       }
+    }
+    if (g_collocate_comm != nullptr) {
+      B200_ASSERT(resident, "the collocate reduction needs device-resident grids");
+      grid_b200_comm_reduce_grid(g_collocate_comm, d_grid, npts, (void *)ls);
     }
     if (!resident) {
       B200_CHECK(cudaMemcpyAsync(grids[l]->host_buffer, d_grid, npts * sizeof(double),

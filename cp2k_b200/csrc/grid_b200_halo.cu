@@ -18,6 +18,9 @@
 // already loaded -- e.g. PyTorch's): the library has no link-time dependency on it and
 // loads on machines without NCCL.
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstring>
@@ -38,6 +41,7 @@ struct NcclApi {
   int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
@@ -67,6 +71,7 @@ static NcclApi &nccl() {
   api.Send = (decltype(api.Send))sym("ncclSend");
   api.Recv = (decltype(api.Recv))sym("ncclRecv");
   api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
   api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
   api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
   api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
@@ -81,12 +86,46 @@ static NcclApi &nccl() {
       b200_fatal("NCCL error", nccl().GetErrorString(r_), __FILE__, __LINE__); \
   } while (0)
 
+// ---- replicated grids in NVLink peer memory ------------------------------------------
+// The sum of a replicated level over the ranks WITHOUT a collective kernel: the grid kernels are
+// persistent and fill every SM, so an NCCL all-reduce enqueued behind one level cannot start
+// before the other levels' kernels have drained (measured: no overlap).  Here every rank's
+// grids live in one cudaMalloc'd slab that all ranks of the node map (CUDA IPC); rank r owns
+// the r-th chunk of each level and
+//   1. pulls that chunk of every peer's grid into a staging buffer   (copy engines, P2P reads)
+//   2. adds the staged chunks into its own                           (one light kernel)
+//   3. pulls every peer's reduced chunk into its own grid            (copy engines)
+// The steps are ordered across ranks by 32-bit step counters in a page of host memory that all
+// ranks map (POSIX shared memory, registered with CUDA): a rank publishes "my level is
+// collocated / my chunk is reduced / I have gathered" with ONE cuStreamWriteValue32, a stream
+// waits for a peer's counter with cuStreamWaitValue32 -- no kernels, no per-peer messages (a
+// first version signalled with 4-byte peer copies: 140 tiny copies per call on the copy engines
+// cost more than the transfers).  Only step 2 needs an SM slot.
+enum PeerFlag : int { PF_DONE = 0, PF_RED = 1, PF_GATH = 2, PF_KINDS = 3 };
+typedef int (*StreamValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+struct PeerGrids {
+  int nlevels = 0;
+  std::vector<size_t> npts, off;       // per level: doubles, offset in the slab (doubles)
+  double *base = nullptr;              // this rank's slab: the levels, then the flag block
+  std::vector<double *> peer_base;     // [rank] (peer_base[rank] == base)
+  unsigned *hflags = nullptr;          // host page shared by the ranks: [rank][kind][level]
+  unsigned *dflags = nullptr;          // its device address
+  size_t hflags_bytes = 0;
+  std::vector<double *> stage;         // per level: (nranks - 1) chunks
+  std::vector<cudaStream_t> cs;
+  std::vector<cudaEvent_t> ev_in, ev_out;
+  std::vector<unsigned> step;          // per level: exchanges enqueued so far
+  StreamValue32Fn wait_value = nullptr, write_value = nullptr;
+};
+
 struct HaloComm {
   void *comm = nullptr;
   int nranks = 1, rank = 0;
   double *tmp = nullptr;  // receive buffer of the halo sum
   size_t tmp_cap = 0;     // doubles
   cudaStream_t stream = nullptr;
+  PeerGrids *peer = nullptr;
+  unsigned long long tag = 0;  // hash of the unique id: names the shared flag page
 };
 
 // ---- the exchange plan of one level ------------------------------------------
@@ -153,6 +192,32 @@ __global__ void halo_add_kernel(double *__restrict__ grid, const double *__restr
     grid[i] += buf[i];
 }
 
+template <int MAXP>
+__global__ void peer_sum_kernel(double *__restrict__ mine, const double *__restrict__ stage, const size_t chunk_stride,
+                                const int npeers, const size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double v = mine[i];
+    for (int k = 0; k < npeers; k++)
+      v += stage[(size_t)k * chunk_stride + i];
+    mine[i] = v;
+  }
+}
+
+// chunk of level l owned by rank r: [lo, hi) in doubles, boundaries on multiples of 32
+static void peer_chunk(const PeerGrids &P, const int nranks, const int l, const int r, size_t &lo, size_t &hi) {
+  const size_t n = P.npts[l], per = ((n + nranks - 1) / nranks + 31) / 32 * 32;
+  lo = std::min(n, per * (size_t)r), hi = std::min(n, per * (size_t)(r + 1));
+}
+
+static int peer_level_of(const HaloComm &H, const double *grid_dev) {
+  if (H.peer == nullptr)
+    return -1;
+  for (int l = 0; l < H.peer->nlevels; l++)
+    if (grid_dev == H.peer->base + H.peer->off[l])
+      return l;
+  return -1;
+}
+
 static void check_slab(const HaloComm &H, const grid_b200_slab &S) {
   B200_ASSERT(S.nranks == H.nranks && S.rank == H.rank, "slab descriptor and communicator disagree");
   B200_ASSERT(S.border >= 0 && S.owned_lo != nullptr && S.owned_hi != nullptr, "incomplete slab descriptor");
@@ -176,18 +241,294 @@ void grid_b200_comm_create(const int nranks, const int rank, const void *unique_
   H->nranks = nranks, H->rank = rank, H->stream = (cudaStream_t)cuda_stream;
   NcclUniqueId id;
   memcpy(&id, unique_id128, sizeof(id));
+  H->tag = 1469598103934665603ull;
+  for (size_t i = 0; i < sizeof(id); i++)
+    H->tag = (H->tag ^ (unsigned char)id.internal[i]) * 1099511628211ull;
   B200_NCCL(nccl().CommInitRank(&H->comm, nranks, id, rank));
   *comm_out = (grid_b200_comm *)H;
+}
+
+// One slab per rank holding all levels, mapped by every rank of the node.  Returns 0 and this
+// rank's per-level device pointers, or non-zero when peer memory is not available (the caller
+// then keeps its own buffers and the sums go through NCCL).
+int grid_b200_comm_share_grids(grid_b200_comm *comm, const int nlevels, const size_t *npts, double **grids_dev_out) {
+  HaloComm &H = *(HaloComm *)comm;
+  B200_ASSERT(H.peer == nullptr, "grids are already shared on this communicator");
+  int dev = 0, ndev = 0;
+  B200_CHECK(cudaGetDevice(&dev));
+  B200_CHECK(cudaGetDeviceCount(&ndev));
+  PeerGrids *P = new PeerGrids();
+  cudaDriverEntryPointQueryResult q1, q2;
+  void *f1 = nullptr, *f2 = nullptr;
+  const bool have_ops = cudaGetDriverEntryPoint("cuStreamWaitValue32", &f1, cudaEnableDefault, &q1) == cudaSuccess &&
+                        cudaGetDriverEntryPoint("cuStreamWriteValue32", &f2, cudaEnableDefault, &q2) == cudaSuccess &&
+                        f1 != nullptr && f2 != nullptr;
+  // every rank must come to the same decision: ok = min over ranks
+  int ok = (have_ops && H.nranks <= ndev) ? 1 : 0;
+  P->wait_value = (StreamValue32Fn)f1, P->write_value = (StreamValue32Fn)f2;
+  P->nlevels = nlevels;
+  size_t total = 0;
+  for (int l = 0; l < nlevels; l++) {
+    P->npts.push_back(npts[l]);
+    P->off.push_back(total);
+    total += (npts[l] + 63) / 64 * 64;
+  }
+  const size_t nflags = (size_t)H.nranks * PF_KINDS * nlevels;
+  const size_t slab_bytes = total * sizeof(double);
+  // the flag page: rank 0 creates it before the first exchange below, the others open it after
+  char shm_name[64];
+  snprintf(shm_name, sizeof(shm_name), "/grid_b200_%016llx", H.tag);
+  P->hflags_bytes = (nflags * sizeof(unsigned) + 4095) / 4096 * 4096;
+  int shm_fd = -1;
+  if (H.rank == 0) {
+    shm_unlink(shm_name);
+    shm_fd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (shm_fd < 0 || ftruncate(shm_fd, (off_t)P->hflags_bytes) != 0)
+      ok = 0;
+  }
+  if (ok && cudaMalloc((void **)&P->base, slab_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0;
+  }
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine, P->base) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0;
+  }
+  // all-gather {ok, handle} over the communicator
+  struct Rec {
+    int ok, pad[15];
+    cudaIpcMemHandle_t h;
+  };
+  static_assert(sizeof(Rec) == 128, "IPC record");
+  Rec rec;
+  memset(&rec, 0, sizeof(rec));
+  rec.ok = ok, rec.h = mine;
+  Rec *d_recs = nullptr;
+  std::vector<Rec> recs(H.nranks);
+  B200_CHECK(cudaMalloc((void **)&d_recs, sizeof(Rec) * H.nranks));
+  B200_CHECK(cudaMemcpy(d_recs + H.rank, &rec, sizeof(Rec), cudaMemcpyHostToDevice));
+  B200_NCCL(nccl().AllGather(d_recs + H.rank, d_recs, sizeof(Rec), /*ncclInt8*/ 0, H.comm, H.stream));
+  B200_CHECK(cudaStreamSynchronize(H.stream));
+  B200_CHECK(cudaMemcpy(recs.data(), d_recs, sizeof(Rec) * H.nranks, cudaMemcpyDeviceToHost));
+  for (const Rec &r : recs)
+    ok = std::min(ok, r.ok);
+  P->peer_base.assign(H.nranks, nullptr);
+  if (ok) {
+    if (H.rank != 0)
+      shm_fd = shm_open(shm_name, O_RDWR, 0600);
+    void *m = (shm_fd >= 0) ? mmap(nullptr, P->hflags_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, shm_fd, 0) : MAP_FAILED;
+    if (m == MAP_FAILED) {
+      ok = 0;
+    } else {
+      P->hflags = (unsigned *)m;
+      if (H.rank == 0)
+        memset(m, 0, P->hflags_bytes);
+      if (cudaHostRegister(m, P->hflags_bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess ||
+          cudaHostGetDevicePointer((void **)&P->dflags, m, 0) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+      }
+    }
+  }
+  if (shm_fd >= 0)
+    close(shm_fd);
+  if (ok) {
+    for (int r = 0; r < H.nranks && ok; r++) {
+      if (r == H.rank) {
+        P->peer_base[r] = P->base;
+      } else if (cudaIpcOpenMemHandle((void **)&P->peer_base[r], recs[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+      }
+    }
+  }
+  // the mapping can fail on one rank only: agree once more
+  int *d_ok = (int *)d_recs;
+  std::vector<int> oks(H.nranks * 32);
+  B200_CHECK(cudaMemcpy(d_ok + 32 * H.rank, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  B200_NCCL(nccl().AllGather(d_ok + 32 * H.rank, d_ok, 128, 0, H.comm, H.stream));
+  B200_CHECK(cudaStreamSynchronize(H.stream));
+  B200_CHECK(cudaMemcpy(oks.data(), d_ok, sizeof(int) * 32 * H.nranks, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < H.nranks; r++)
+    ok = std::min(ok, oks[32 * r]);
+  cudaFree(d_recs);
+  if (H.rank == 0)
+    shm_unlink(shm_name);  // everybody has opened it (or given up)
+  if (!ok) {
+    if (P->hflags != nullptr) {
+      cudaHostUnregister(P->hflags);
+      munmap(P->hflags, P->hflags_bytes);
+    }
+    for (int r = 0; r < H.nranks; r++)
+      if (r != H.rank && P->peer_base[r] != nullptr)
+        cudaIpcCloseMemHandle(P->peer_base[r]);
+    cudaFree(P->base);
+    delete P;
+    return 1;
+  }
+  B200_CHECK(cudaMemset(P->base, 0, slab_bytes));
+  int prio_least = 0, prio_greatest = 0;
+  B200_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  for (int l = 0; l < nlevels; l++) {
+    size_t lo, hi;
+    peer_chunk(*P, H.nranks, l, 0, lo, hi);
+    double *st = nullptr;
+    B200_CHECK(cudaMalloc((void **)&st, std::max<size_t>((hi - lo) * (H.nranks - 1), 1) * sizeof(double)));
+    P->stage.push_back(st);
+    cudaStream_t cs;
+    cudaEvent_t a, b;
+    B200_CHECK(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, prio_greatest));
+    B200_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    B200_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    P->cs.push_back(cs), P->ev_in.push_back(a), P->ev_out.push_back(b);
+    P->step.push_back(0);
+    grids_dev_out[l] = P->base + P->off[l];
+  }
+  B200_CHECK(cudaDeviceSynchronize());
+  // nobody may signal into a flag block that is not zeroed yet
+  B200_CHECK(cudaMalloc((void **)&d_ok, 128));
+  B200_NCCL(nccl().AllReduce(d_ok, d_ok, 1, /*ncclInt32*/ 2, kNcclSum, H.comm, H.stream));
+  B200_CHECK(cudaStreamSynchronize(H.stream));
+  cudaFree(d_ok);
+  H.peer = P;
+  return 0;
+}
+
+#define B200_DRV(cmd)                                                          \
+  do {                                                                         \
+    const int r_ = (cmd);                                                      \
+    if (r_ != 0)                                                               \
+      b200_fatal("CUDA driver error in a stream memory operation", #cmd, __FILE__, __LINE__); \
+  } while (0)
+
+// Called before a shared grid is overwritten (the collocate's memset): the peers must have
+// pulled this rank's reduced chunk of the previous exchange.
+void grid_b200_comm_begin_grid(grid_b200_comm *comm, double *grid_dev, void *cuda_stream) {
+  HaloComm &H = *(HaloComm *)comm;
+  const int l = peer_level_of(H, grid_dev);
+  if (l < 0)
+    return;
+  PeerGrids &P = *H.peer;
+  if (P.step[l] == 0)
+    return;
+  for (int p = 0; p < H.nranks; p++)
+    if (p != H.rank)
+      B200_DRV(P.wait_value((cudaStream_t)cuda_stream,
+                            (unsigned long long)(P.dflags + ((size_t)p * PF_KINDS + PF_GATH) * P.nlevels + l), P.step[l],
+                            /*CU_STREAM_WAIT_VALUE_GEQ*/ 0));
+}
+
+// Sum of a replicated grid over the ranks, enqueued behind the work of `cuda_stream`; the stream
+// continues when this rank holds the sum.  Shared grids go through peer memory, others through NCCL.
+void grid_b200_comm_reduce_grid(grid_b200_comm *comm, double *grid_dev, const size_t count, void *cuda_stream) {
+  HaloComm &H = *(HaloComm *)comm;
+  const int l = peer_level_of(H, grid_dev);
+  if (l < 0 || H.nranks == 1) {
+    grid_b200_comm_allreduce(comm, grid_dev, count, cuda_stream);
+    return;
+  }
+  PeerGrids &P = *H.peer;
+  B200_ASSERT(count == P.npts[l], "shared grid: size differs from the one it was created with");
+  cudaStream_t ps = (cudaStream_t)cuda_stream, cs = P.cs[l];
+  const unsigned step = ++P.step[l];
+  const int me = H.rank, n = H.nranks;
+  auto flag_of = [&](const int src, const int kind) { return P.dflags + ((size_t)src * PF_KINDS + kind) * P.nlevels + l; };
+  auto signal = [&](const int kind, cudaStream_t st) {
+    B200_DRV(P.write_value(st, (unsigned long long)flag_of(me, kind), step, 0));
+  };
+  auto wait_for = [&](const int p, const int kind) {
+    B200_DRV(P.wait_value(cs, (unsigned long long)flag_of(p, kind), step, 0));
+  };
+  // my level is complete
+  signal(PF_DONE, ps);
+  B200_CHECK(cudaEventRecord(P.ev_in[l], ps));
+  B200_CHECK(cudaStreamWaitEvent(cs, P.ev_in[l], 0));
+  // 1. the peers' contributions to my chunk
+  size_t lo, hi;
+  peer_chunk(P, n, l, me, lo, hi);
+  size_t lo0, hi0;
+  peer_chunk(P, n, l, 0, lo0, hi0);
+  const size_t stride = hi0 - lo0;
+  int k = 0;
+  for (int d = 1; d < n; d++, k++) {  // start with the next rank: spreads the reads over the peers
+    const int p = (me + d) % n;
+    wait_for(p, PF_DONE);
+    if (hi > lo)
+      B200_CHECK(cudaMemcpyAsync(P.stage[l] + (size_t)k * stride, P.peer_base[p] + P.off[l] + lo, (hi - lo) * sizeof(double),
+                                 cudaMemcpyDefault, cs));
+  }
+  // 2. add them
+  if (hi > lo) {
+    const size_t cnt = hi - lo;
+    peer_sum_kernel<0><<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 2), 256, 0, cs>>>(
+        P.base + P.off[l] + lo, P.stage[l], stride, n - 1, cnt);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  signal(PF_RED, cs);
+  // 3. the other chunks, reduced by their owners
+  for (int d = 1; d < n; d++) {
+    const int p = (me + d) % n;
+    size_t plo, phi;
+    peer_chunk(P, n, l, p, plo, phi);
+    wait_for(p, PF_RED);
+    if (phi > plo)
+      B200_CHECK(cudaMemcpyAsync(P.base + P.off[l] + plo, P.peer_base[p] + P.off[l] + plo, (phi - plo) * sizeof(double),
+                                 cudaMemcpyDefault, cs));
+  }
+  signal(PF_GATH, cs);
+  B200_CHECK(cudaEventRecord(P.ev_out[l], cs));
+  B200_CHECK(cudaStreamWaitEvent(ps, P.ev_out[l], 0));
 }
 
 void grid_b200_comm_destroy(grid_b200_comm *comm) {
   if (comm == nullptr)
     return;
   HaloComm *H = (HaloComm *)comm;
+  if (H->peer != nullptr) {
+    PeerGrids *P = H->peer;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < H->nranks; r++)
+      if (r != H->rank)
+        cudaIpcCloseMemHandle(P->peer_base[r]);
+    for (size_t l = 0; l < P->cs.size(); l++) {
+      cudaStreamDestroy(P->cs[l]);
+      cudaEventDestroy(P->ev_in[l]), cudaEventDestroy(P->ev_out[l]);
+      cudaFree(P->stage[l]);
+    }
+    cudaHostUnregister(P->hflags);
+    munmap(P->hflags, P->hflags_bytes);
+    cudaFree(P->base);
+    delete P;
+  }
   if (H->comm)
     nccl().CommDestroy(H->comm);
   cudaFree(H->tmp);
   delete H;
+}
+
+// Sum of a replicated buffer over the ranks, enqueued on the given stream (NCCL orders the
+// operations of a communicator in issue order, whichever streams they are issued on).
+void grid_b200_comm_allreduce(grid_b200_comm *comm, double *buf_dev, const size_t count, void *cuda_stream) {
+  HaloComm &H = *(HaloComm *)comm;
+  if (H.nranks > 1 && count > 0)
+    B200_NCCL(nccl().AllReduce(buf_dev, buf_dev, count, kNcclDouble, kNcclSum, H.comm, (cudaStream_t)cuda_stream));
+}
+
+// The same for several buffers (the levels of a call) as ONE grouped NCCL operation: one kernel
+// launch instead of one per level.
+void grid_b200_comm_allreduce_levels(grid_b200_comm *comm, const int n, double *const *bufs_dev, const size_t *counts,
+                                     void *cuda_stream) {
+  HaloComm &H = *(HaloComm *)comm;
+  if (H.nranks <= 1)
+    return;
+  B200_NCCL(nccl().GroupStart());
+  for (int i = 0; i < n; i++)
+    if (counts[i] > 0)
+      B200_NCCL(nccl().AllReduce(bufs_dev[i], bufs_dev[i], counts[i], kNcclDouble, kNcclSum, H.comm, (cudaStream_t)cuda_stream));
+  B200_NCCL(nccl().GroupEnd());
 }
 
 // Messages this rank takes part in, in plan order; for tests of the plan on a CPU.

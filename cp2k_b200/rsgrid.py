@@ -485,6 +485,48 @@ class HaloComm:
             self._slabs[key] = c_slab(sl, self.rank, self.world)
         return self._slabs[key][0]
 
+    def allreduce(self, buf, stream_ptr: int = 0) -> None:
+        """Sum of a replicated CUDA float64 tensor over the ranks, on the given stream."""
+        f = self.L.grid_b200_comm_allreduce
+        f.restype, f.argtypes = None, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        f(self.handle, C.c_void_p(buf.data_ptr()), buf.numel(), C.c_void_p(stream_ptr))
+
+    def share_grids(self, npts):
+        """Replicated grids in NVLink peer memory (`grid_b200_comm_share_grids`): this rank's
+        grids as CUDA float64 tensors over the library's slab, or None when peer memory is not
+        available (collective over the ranks)."""
+        import torch
+
+        f = self.L.grid_b200_comm_share_grids
+        f.restype, f.argtypes = C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+        n = len(npts)
+        sizes = (C.c_size_t * n)(*[int(x) for x in npts])
+        ptrs = (C.c_void_p * n)()
+        if f(self.handle, n, sizes, ptrs) != 0:
+            return None
+
+        class _Dev:  # zero-copy view of library-owned device memory
+            def __init__(self, ptr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        return [torch.as_tensor(_Dev(int(ptrs[i]), int(npts[i])), device="cuda") for i in range(n)]
+
+    def allreduce_levels(self, bufs, stream_ptr: int = 0) -> None:
+        """Sums of several replicated CUDA float64 tensors as one grouped NCCL operation."""
+        f = self.L.grid_b200_comm_allreduce_levels
+        f.restype, f.argtypes = None, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
+        n = len(bufs)
+        ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in bufs])
+        counts = (C.c_size_t * n)(*[b.numel() for b in bufs])
+        f(self.handle, n, ptrs, counts, C.c_void_p(stream_ptr))
+
+    def set_collocate_reduce(self, on: bool = True) -> None:
+        """Replicated rs_grids: `grid_b200_collocate_task_list` sums every level over the ranks
+        itself, each level's all-reduce overlapping the other levels' kernels."""
+        f = self.L.grid_b200_set_collocate_reduce
+        f.restype, f.argtypes = None, [C.c_void_p]
+        f(self.handle if on else None)
+
     def halo_sum(self, grid, sl: SlabLevel) -> None:
         """`grid`: this rank's local grid of the level, a contiguous CUDA float64 tensor."""
         self.L.grid_b200_halo_sum(self.handle, C.byref(self._slab(sl)), C.c_void_p(grid.data_ptr()))

@@ -185,6 +185,36 @@ void grid_b200_comm_unique_id(void *out128);
 void grid_b200_comm_create(const int nranks, const int rank, const void *unique_id128, void *cuda_stream,
                            grid_b200_comm **comm_out);
 void grid_b200_comm_destroy(grid_b200_comm *comm);
+
+/* Sum of a replicated device buffer over the ranks of `comm`, enqueued on `cuda_stream`. */
+void grid_b200_comm_allreduce(grid_b200_comm *comm, double *buf_dev, const size_t count, void *cuda_stream);
+/* The same for n buffers (the levels of a call) as one grouped NCCL operation. */
+void grid_b200_comm_allreduce_levels(grid_b200_comm *comm, const int n, double *const *bufs_dev, const size_t *counts,
+                                     void *cuda_stream);
+
+/* Replicated rs_grids (what CP2K uses for small systems and coarse levels,
+ * src/pw/realspace_grid_types.F:763-825: every rank collocates its tasks onto full-size grids and
+ * the grids are summed over the ranks): with a communicator set here,
+ * grid_b200_collocate_task_list sums every level over the ranks itself, in device-resident mode
+ * -- a level's sum is enqueued behind that level's kernels, on the level's stream.  NULL (default)
+ * switches the sum off.  Measured on 8 B200: the grid kernels are persistent
+ * and fill every SM, so an NCCL kernel enqueued this way does not start before the other levels
+ * drain -- no faster than one grouped all-reduce after the call, which stays the default. */
+void grid_b200_set_collocate_reduce(grid_b200_comm *comm);
+
+/* Replicated grids in NVLink peer memory.  share_grids allocates this rank's grids of all levels
+ * (npts[l] doubles each) in one slab that every rank of the node maps (CUDA IPC) and returns the
+ * per-level device pointers; the caller uses them as the device_buffer of its grid buffers.
+ * reduce_grid then sums such a grid over the ranks without a collective kernel: every rank pulls
+ * its chunk of the peers' grids with the copy engines, adds them with one light kernel and pulls
+ * the peers' reduced chunks, ordered by step counters in peer memory (cuStreamWaitValue32) --
+ * all of it behind the work of `cuda_stream` and beside whatever runs on other streams.  Grids
+ * that were not shared go through NCCL.  begin_grid must be enqueued before a shared grid is
+ * overwritten again (grid_b200_collocate_task_list does both when set_collocate_reduce is on).
+ * share_grids returns non-zero when peer memory is unavailable; collective over the ranks. */
+int grid_b200_comm_share_grids(grid_b200_comm *comm, const int nlevels, const size_t *npts, double **grids_dev_out);
+void grid_b200_comm_begin_grid(grid_b200_comm *comm, double *grid_dev, void *cuda_stream);
+void grid_b200_comm_reduce_grid(grid_b200_comm *comm, double *grid_dev, const size_t count, void *cuda_stream);
 void grid_b200_halo_sum(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev);
 void grid_b200_halo_fill(grid_b200_comm *comm, const grid_b200_slab *slab, double *grid_dev);
 /* All levels of a call in one grouped NCCL operation (what a level's exchange costs is the

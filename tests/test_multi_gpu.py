@@ -1,5 +1,7 @@
 """The multi-GPU product path on hardware: NCCL + the B200 kernels + the exchange step
-(all-reduce of replicated grids, or the z-slab halo sum / fill and the owner reduction of H)
+(sum of replicated grids -- one grouped NCCL all-reduce, per-level all-reduces inside collocate, or
+the copy-engine exchange through NVLink peer memory --, or the z-slab halo sum / fill and the owner
+reduction of H)
 against a single-GPU run of the full task list, on H2O-64 at 2 ranks, for every decomposition
 bench.py offers.  Needs two GPUs on the box (skipped otherwise); the same check runs untimed
 inside every `bench.py --gpus N` (N > 1) run on the benchmark's own workload."""
@@ -14,8 +16,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("extra", [[], ["--decomp", "slab"], ["--decomp", "slab", "--slab-compact"]],
-                         ids=["blocks", "slab", "slab-compact"])
+@pytest.mark.parametrize("extra", [[], ["--allreduce", "fused"], ["--allreduce", "peer"], ["--decomp", "slab"],
+                                   ["--decomp", "slab", "--slab-compact"]],
+                         ids=["blocks", "blocks-fused-nccl", "blocks-peer-memory", "slab", "slab-compact"])
 def test_two_ranks_match_one_gpu(b200, extra):
     import torch
 
