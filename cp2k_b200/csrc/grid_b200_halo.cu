@@ -114,6 +114,11 @@ struct PeerGrids {
   std::vector<double *> stage;         // per level: (nranks - 1) chunks
   std::vector<cudaStream_t> cs;
   std::vector<cudaEvent_t> ev_in, ev_out;
+  // one more stream per (level, peer): the pulls from the peers run side by side on the copy
+  // engines (in one stream they are serialised at the rate of a single engine: measured 0.56 ms
+  // exposed per call at 8 GPUs)
+  std::vector<cudaStream_t> pull;      // [level * (nranks - 1) + k]
+  std::vector<cudaEvent_t> ev_pull;    // [(level * (nranks - 1) + k) * 2 + phase]
   std::vector<unsigned> step;          // per level: exchanges enqueued so far
   StreamValue32Fn wait_value = nullptr, write_value = nullptr;
 };
@@ -192,13 +197,19 @@ __global__ void halo_add_kernel(double *__restrict__ grid, const double *__restr
     grid[i] += buf[i];
 }
 
-template <int MAXP>
-__global__ void peer_sum_kernel(double *__restrict__ mine, const double *__restrict__ stage, const size_t chunk_stride,
-                                const int npeers, const size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+// 64-thread CTAs with at most 32 registers per thread: 2048 registers, what the persistent grid
+// kernels (4 CTAs x 128 threads x 124 registers) leave free on an SM -- the sum does not have to
+// wait for one of them to exit.
+constexpr int kPeerSumThreads = 64;
+__global__ void __launch_bounds__(kPeerSumThreads, 32)
+peer_sum_kernel(double *__restrict__ mine, const double *__restrict__ stage, const unsigned chunk_stride, const int npeers,
+                const unsigned n) {
+  for (unsigned i = blockIdx.x * kPeerSumThreads + threadIdx.x; i < n; i += gridDim.x * kPeerSumThreads) {
     double v = mine[i];
-    for (int k = 0; k < npeers; k++)
-      v += stage[(size_t)k * chunk_stride + i];
+    const double *p = stage + i;
+#pragma unroll 1
+    for (int k = 0; k < npeers; k++, p += chunk_stride)
+      v += *p;
     mine[i] = v;
   }
 }
@@ -384,6 +395,16 @@ int grid_b200_comm_share_grids(grid_b200_comm *comm, const int nlevels, const si
     B200_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     P->cs.push_back(cs), P->ev_in.push_back(a), P->ev_out.push_back(b);
     P->step.push_back(0);
+    for (int k = 0; k < H.nranks - 1; k++) {
+      cudaStream_t q;
+      B200_CHECK(cudaStreamCreateWithPriority(&q, cudaStreamNonBlocking, prio_greatest));
+      P->pull.push_back(q);
+      for (int ph = 0; ph < 2; ph++) {
+        cudaEvent_t e;
+        B200_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        P->ev_pull.push_back(e);
+      }
+    }
     grids_dev_out[l] = P->base + P->off[l];
   }
   B200_CHECK(cudaDeviceSynchronize());
@@ -438,8 +459,8 @@ void grid_b200_comm_reduce_grid(grid_b200_comm *comm, double *grid_dev, const si
   auto signal = [&](const int kind, cudaStream_t st) {
     B200_DRV(P.write_value(st, (unsigned long long)flag_of(me, kind), step, 0));
   };
-  auto wait_for = [&](const int p, const int kind) {
-    B200_DRV(P.wait_value(cs, (unsigned long long)flag_of(p, kind), step, 0));
+  auto wait_for = [&](cudaStream_t st, const int p, const int kind) {
+    B200_DRV(P.wait_value(st, (unsigned long long)flag_of(p, kind), step, 0));
   };
   // my level is complete
   signal(PF_DONE, ps);
@@ -451,32 +472,42 @@ void grid_b200_comm_reduce_grid(grid_b200_comm *comm, double *grid_dev, const si
   size_t lo0, hi0;
   peer_chunk(P, n, l, 0, lo0, hi0);
   const size_t stride = hi0 - lo0;
-  int k = 0;
-  for (int d = 1; d < n; d++, k++) {  // start with the next rank: spreads the reads over the peers
-    const int p = (me + d) % n;
-    wait_for(p, PF_DONE);
+  for (int d = 1; d < n; d++) {  // start with the next rank: spreads the reads over the peers
+    const int p = (me + d) % n, k = d - 1;
+    cudaStream_t q = P.pull[(size_t)l * (n - 1) + k];
+    cudaEvent_t e = P.ev_pull[((size_t)l * (n - 1) + k) * 2 + 0];
+    B200_CHECK(cudaStreamWaitEvent(q, P.ev_in[l], 0));  // (the staging buffer is free: cs has passed the last sum)
+    wait_for(q, p, PF_DONE);
     if (hi > lo)
       B200_CHECK(cudaMemcpyAsync(P.stage[l] + (size_t)k * stride, P.peer_base[p] + P.off[l] + lo, (hi - lo) * sizeof(double),
-                                 cudaMemcpyDefault, cs));
+                                 cudaMemcpyDefault, q));
+    B200_CHECK(cudaEventRecord(e, q));
+    B200_CHECK(cudaStreamWaitEvent(cs, e, 0));
   }
   // 2. add them
   if (hi > lo) {
     const size_t cnt = hi - lo;
-    peer_sum_kernel<0><<<(unsigned)std::min<size_t>((cnt + 255) / 256, 148 * 2), 256, 0, cs>>>(
-        P.base + P.off[l] + lo, P.stage[l], stride, n - 1, cnt);
+    B200_ASSERT(cnt < ((size_t)1 << 31) && stride < ((size_t)1 << 31), "shared grid too large for the sum kernel");
+    peer_sum_kernel<<<(unsigned)std::min<size_t>((cnt + kPeerSumThreads - 1) / kPeerSumThreads, 148 * 8), kPeerSumThreads, 0,
+                      cs>>>(P.base + P.off[l] + lo, P.stage[l], (unsigned)stride, n - 1, (unsigned)cnt);
     B200_CHECK(cudaGetLastError());
     count_launch();
   }
   signal(PF_RED, cs);
-  // 3. the other chunks, reduced by their owners
+  // 3. the other chunks, reduced by their owners (a peer's RED also says that it has read my
+  //    contribution to its chunk, which the pull overwrites)
   for (int d = 1; d < n; d++) {
-    const int p = (me + d) % n;
+    const int p = (me + d) % n, k = d - 1;
+    cudaStream_t q = P.pull[(size_t)l * (n - 1) + k];
+    cudaEvent_t e = P.ev_pull[((size_t)l * (n - 1) + k) * 2 + 1];
     size_t plo, phi;
     peer_chunk(P, n, l, p, plo, phi);
-    wait_for(p, PF_RED);
+    wait_for(q, p, PF_RED);
     if (phi > plo)
       B200_CHECK(cudaMemcpyAsync(P.base + P.off[l] + plo, P.peer_base[p] + P.off[l] + plo, (phi - plo) * sizeof(double),
-                                 cudaMemcpyDefault, cs));
+                                 cudaMemcpyDefault, q));
+    B200_CHECK(cudaEventRecord(e, q));
+    B200_CHECK(cudaStreamWaitEvent(cs, e, 0));
   }
   signal(PF_GATH, cs);
   B200_CHECK(cudaEventRecord(P.ev_out[l], cs));
@@ -493,6 +524,10 @@ void grid_b200_comm_destroy(grid_b200_comm *comm) {
     for (int r = 0; r < H->nranks; r++)
       if (r != H->rank)
         cudaIpcCloseMemHandle(P->peer_base[r]);
+    for (cudaStream_t q : P->pull)
+      cudaStreamDestroy(q);
+    for (cudaEvent_t e : P->ev_pull)
+      cudaEventDestroy(e);
     for (size_t l = 0; l < P->cs.size(); l++) {
       cudaStreamDestroy(P->cs[l]);
       cudaEventDestroy(P->ev_in[l]), cudaEventDestroy(P->ev_out[l]);
