@@ -607,6 +607,14 @@ def main():
         # integrate (device_buffer authoritative); this rank's P blocks come from
         # pinned host memory and its H blocks go back to it every step
         lib.set_device_resident(True)
+        if slab_levels is None:
+            # through the public API: P and H are host-only buffers (the library pipelines
+            # their copies against its coefficient kernels and returns when H has landed)
+            tl.collocate(FUNC, pab_e, grids)
+            exchange(grids)
+            tl.integrate(TAU, pab_e if args.forces else None, grids, hab_e, forces, virial)
+            return
+        # slab modes: the partial H blocks are summed into their owners on the device first
         pab.device.copy_(pin_pab, non_blocking=True)
         tl.collocate(FUNC, pab, grids)
         exchange(grids)
@@ -636,15 +644,12 @@ def main():
     e2e_ph_ms = None
     if world == 1:
         lib.set_device_resident(True)
-        pin_pab1 = torch.from_numpy(pab_h.host).pin_memory()
-        pin_hab1 = torch.empty(wl.pab_len, dtype=torch.float64).pin_memory()
 
         def step_ph():
-            pab.device.copy_(pin_pab1, non_blocking=True)
-            tl.collocate(FUNC, pab, grids)
-            tl.integrate(TAU, pab if args.forces else None, grids, hab, forces, virial)
-            pin_hab1.copy_(hab.device[: wl.pab_len], non_blocking=True)
-            torch.cuda.synchronize()
+            # host-only P and H buffers, grids with an authoritative device_buffer: the library
+            # pipelines the P / H copies and returns when H has landed
+            tl.collocate(FUNC, pab_e, grids)
+            tl.integrate(TAU, pab_e if args.forces else None, grids, hab_e, forces, virial)
 
         step_ph()
         t0 = time.perf_counter()

@@ -976,7 +976,8 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   CL.sphi_pool = tl.d_sphi.p, CL.coef_offsets = tl.d_coef_off[dl].p, CL.coef = tl.d_coef.p;
   CL.cijk_T = tl.d_Tptrs.p, CL.glists = tl.d_glists.p, CL.stream = s;
   const double *d_pab = nullptr;
-  if (g_device_resident && use_caller_device(pab_blocks)) {
+  const bool pab_from_host = !(g_device_resident && use_caller_device(pab_blocks));
+  if (!pab_from_host) {
     d_pab = pab_blocks->device_buffer;
     ScopedTimer tm(T_PAB2COEF, s);
     for (int k = 0; k < kNumSizeClasses; k++) {
@@ -1074,6 +1075,8 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
     }
     if (!g_device_resident || any_host)
       B200_CHECK(cudaStreamSynchronize(s));
+    else if (pab_from_host && !tl.chunks.empty())  // the caller may change host P once the call has returned
+      B200_CHECK(cudaEventSynchronize(tl.ev_chunk[tl.chunks.size() - 1]));
     return;
   }
 
@@ -1136,6 +1139,8 @@ void grid_b200_collocate_task_list(const grid_b200_task_list *ptr, const int fun
   // copies back must have landed when the call returns
   if (!g_device_resident || any_host_copy)
     B200_CHECK(cudaStreamSynchronize(s));
+  else if (pab_from_host && !tl.chunks.empty())  // the caller may change host P once the call has returned
+    B200_CHECK(cudaEventSynchronize(tl.ev_chunk[tl.chunks.size() - 1]));
 }
 
 void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool compute_tau,
@@ -1349,8 +1354,12 @@ void grid_b200_integrate_task_list(const grid_b200_task_list *ptr, const bool co
   if (do_v)
     B200_CHECK(cudaMemcpyAsync(virial, tl.d_fv.p + (size_t)3 * natoms, sizeof(double) * 9,
                                cudaMemcpyDeviceToHost, s));
-  // (hab not resident: its copy back to host_buffer must have landed on return)
-  if (!g_device_resident || !hab_resident || do_f || do_v)
+  // (hab not resident: its copy back to host_buffer must have landed on return; grids taken from
+  // host_buffer: the caller may change them once the call has returned)
+  bool grids_from_host = false;
+  for (int l = 0; l < nlevels; l++)
+    grids_from_host = grids_from_host || !(g_device_resident && use_caller_device(grids[l]));
+  if (!g_device_resident || !hab_resident || grids_from_host || do_f || do_v)
     B200_CHECK(cudaStreamSynchronize(s));
 }
 
