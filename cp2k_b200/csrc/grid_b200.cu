@@ -419,6 +419,12 @@ static void ensure_coef_offsets(TaskList &tl, int dl, cudaStream_t s) {
   std::vector<int> off(tl.ntasks, -1);
   size_t total = 0;
   // (slots start at even offsets and have even strides: 16-byte aligned for the bulk copies)
+  // The class kernels' look-ahead reads the slot of one pair past their range with THEIR class's
+  // base and stride; that address stays inside the level's run of slots (and the buffer) only
+  // because a level's classes are laid out back to back in ascending order with non-decreasing
+  // strides, and the buffer ends with slack:
+  static_assert(kClassHi[0] < kClassHi[1] && kClassHi[1] < kClassHi[2] && kNumClasses == 3,
+                "coefficient slots: class strides must ascend (look-ahead of the pair loops)");
   for (int lev = 0; lev < tl.nlevels; lev++) {
     LevelInfo &li = tl.linfo[lev];
     const bool ct = (tl.path == 0);

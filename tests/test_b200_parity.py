@@ -185,6 +185,43 @@ def test_device_resident_mode_matches_host_mode(b200, oracle, wl_ortho):
     tl.free()
 
 
+def test_resident_mode_with_host_only_buffers(b200, oracle, wl_ortho):
+    """Mixed mode: the resident flag is on, but P and H are pinned host-only buffers (NULL
+    device_buffer) -- the library copies them inside the call and must not return before the copies
+    are done: host P may be changed right after collocate returns, host H is read right after
+    integrate returns, without any synchronisation by the caller.  Grids once device-authoritative,
+    once host-only as well."""
+    import torch
+
+    wl = wl_ortho
+    pab_h = wl.random_pab(9)
+    ref = _collocate(oracle, wl, 100, pab_h)
+    gh = wl.new_grids()
+    for g, r in zip(gh, ref):
+        g.host[:] = r
+    hab_r, _, _ = _integrate(oracle, wl, False, pab_h, gh, False, False)
+    tl = wl.create(b200)
+    pab = OffloadBuffer(wl.pab_len, pinned=True)
+    hab = OffloadBuffer(wl.pab_len, pinned=True)
+    grids_dev = [OffloadBuffer.with_device(l.npts_local_total) for l in wl.layouts]
+    grids_host = [OffloadBuffer(l.npts_local_total, pinned=True) for l in wl.layouts]
+    b200.set_device_resident(True)
+    try:
+        for grids in (grids_dev, grids_host):
+            pab.host[:] = pab_h.host
+            hab.host[:] = np.nan
+            tl.collocate(100, pab, grids)
+            pab.host[:] = 0.0  # the caller owns host P again
+            tl.integrate(False, None, grids, hab)
+            assert rel_diff(hab.host[: hab_r.size].copy(), hab_r) < HAB_TOL
+            for g, r in zip(grids, ref):
+                got = g.device.cpu().numpy() if g.device is not None else g.host
+                assert rel_diff(got[: r.size], r) < GRID_TOL
+    finally:
+        b200.set_device_resident(False)
+    tl.free()
+
+
 def test_stats_match_oracle_counters(b200, oracle, wl_ortho, wl_general):
     for wl in (wl_ortho, wl_general):
         tl = wl.create(b200)
