@@ -54,3 +54,25 @@ def test_product_arm_fails_loudly_without_gpu():
     out = _run("--workload", "H2O-64", "--steps", "1", "--warmup", "1", "--no-cpu-baseline")
     assert out.returncode != 0
     assert not any(l.startswith("{") for l in out.stdout.splitlines())  # no number without the device
+
+
+def test_committed_product_line_carries_the_contract_keys():
+    """The product arm needs a GPU; its latest line measured on a B200 is committed under
+    profiles/ -- the keys the driver and the judge read must all be there."""
+    path = os.path.join(ROOT, "profiles", "r02", "bench_h2o256_1gpu_r02e.json")
+    d = json.loads([l for l in open(path).read().splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline",
+                "create_task_list"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor", "fp64") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "reference" and c["cores"] >= 1 and c["same_config"] is True
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["create_task_list"]["ms"] == min(d["create_task_list"]["all_ms"])
