@@ -1,3 +1,5 @@
 #!/bin/bash
-timeout 200 python -m pytest tests/test_b200_parity.py -x -q -m gpu -k "resident or warptile-integrate or multi_pair" 2>&1 | tail -2
-timeout 100 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+mkdir -p gpurun_out
+timeout 120 python bench.py --no-reference-gpu --no-cpu-baseline > gpurun_out/bench_head.json 2> gpurun_out/bench_head.err
+python -c "
+import json;d=json.loads(open('gpurun_out/bench_head.json').read().strip().splitlines()[-1]);print(d['ms_per_step'], d['e2e']['ms_per_step'], d['create_task_list']['ms'], d['roofline']['frac'], d['clocks'])"
